@@ -1,0 +1,64 @@
+"""Synthetic workloads of the reference benches (benches/lj.rs:15-34, 59-66).
+
+The reference draws its points from rand-0.8 `StdRng::seed_from_u64(3079380797442975911)`;
+that stream is not reproducible without the crate (and no golden point is stored upstream),
+so we reproduce the DISTRIBUTION -- uniform in the centred box -- with a counter-based
+splitmix64 stream that is identical on the host (numpy, here) and needs no state.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+REFERENCE_SEED = 3079380797442975911  # benches/lj.rs:22 (reused as *our* seed)
+CUTOFF = 10.0                         # benches/lj.rs:60
+
+
+def lj_box(n: int, cutoff: float = CUTOFF):
+    """Edge lengths (a, b, c) of the benchmark box: 10 particles per cutoff^3 (benches/lj.rs:60-64)."""
+    conc = 10.0 / cutoff**3
+    a = 3.0 * cutoff
+    b = 3.0 * cutoff
+    c = (float(n) / conc) / a / b
+    return a, b, c
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def uniform01(n_values: int, seed: int = REFERENCE_SEED, offset: int = 0) -> np.ndarray:
+    """n_values doubles in [0, 1) with 53 random bits each (what rand's `Standard` f64 yields)."""
+    with np.errstate(over="ignore"):
+        ctr = np.arange(offset, offset + n_values, dtype=np.uint64) + np.uint64(seed % (1 << 64))
+    bits = _splitmix64(ctr) >> np.uint64(11)
+    return bits.astype(np.float64) * (1.0 / (1 << 53))
+
+
+def generate_points_random(n: int, vol=None, origin=(0.0, 0.0, 0.0), seed: int = REFERENCE_SEED,
+                           dtype=np.float64, first: int = 0) -> np.ndarray:
+    """(u - 0.5 + origin) * vol per component, u ~ U[0,1) (benches/lj.rs:15-34).
+
+    `first` offsets the particle counter so slabs/chunks of one global cloud can be generated
+    independently.  f32 clouds are the f64 cloud cast, as examples/cachemisses.rs:61-63 does.
+    """
+    if vol is None:
+        vol = lj_box(n)
+    u = uniform01(3 * n, seed, 3 * first).reshape(n, 3)
+    pts = (u - 0.5 + np.asarray(origin, dtype=np.float64)) * np.asarray(vol, dtype=np.float64)
+    return np.ascontiguousarray(pts.astype(dtype, copy=False))
+
+
+def presort_by_z(points: np.ndarray) -> np.ndarray:
+    """examples/cachemisses.rs:57-59: sort_unstable_by z."""
+    return np.ascontiguousarray(points[np.argsort(points[:, 2], kind="stable")])
+
+
+def perturb(points: np.ndarray, step: int, amplitude: float, seed: int = REFERENCE_SEED) -> np.ndarray:
+    """x += U(-amplitude, amplitude) per coordinate; our definition (the reference has none)."""
+    n = points.shape[0]
+    u = uniform01(points.size, seed ^ 0x5DEECE66D, (step + 1) * points.size).reshape(n, -1)
+    return np.ascontiguousarray((points.astype(np.float64) + (2.0 * u - 1.0) * amplitude).astype(points.dtype))
