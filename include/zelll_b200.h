@@ -1,0 +1,180 @@
+/* zelll_b200.h -- C ABI of the B200-native cell-list engine (libzelll_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of microscopic-image-analysis/zelll v0.5.0:
+ *   CellGrid::new / rebuild / rebuild_mut  ->  particle_pairs / par_particle_pairs
+ *   ->  distance filter + pair list / Lennard-Jones energy.
+ *
+ * The reference is pure Rust and has no FFI of its own; the entry points below are what a
+ * `zelll-b200-sys` crate (Rust `extern "C"`), the PyO3 module and the ctypes front end in
+ * zelll_b200/ bind (INTEGRATION.md shows the stubs).  Each entry cites the reference item
+ * (file:line under the reference tree) it replaces.
+ *
+ * Conventions
+ *   - every call returns a zb_status (0 = ok); nothing throws or aborts across the boundary
+ *     (the reference panics instead: src/cellgrid.rs:227-229, src/cellgrid/util.rs:229-232);
+ *   - `xyz` is a packed [n][ndim] array of f32 or f64 (the layout of `[T; N]` particles,
+ *     src/lib.rs:236-244); particle labels are the enumerate() order 0..n-1
+ *     (src/lib.rs:225-234, benches/lj.rs:71-78);
+ *   - input/output pointers may be HOST or DEVICE memory (detected); device pointers make the
+ *     call asynchronous on the handle's stream, host pointers synchronise it;
+ *   - the handle owns all device memory and reuses it across rebuilds (the rebuild_mut
+ *     contract, src/cellgrid.rs:251-252); one handle = one stream, not re-entrant; distinct
+ *     handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device zb_grid_create fails with ZB_ERR_CUDA.
+ */
+#ifndef ZELLL_B200_H
+#define ZELLL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_ABI_VERSION 1
+
+typedef struct zb_grid zb_grid; /* opaque: CellGrid<(usize,[T;N]),N,T>, src/cellgrid.rs:112-126 */
+
+enum zb_dtype { ZB_F32 = 0, ZB_F64 = 1 };
+
+/* distance filter applied to the candidate pairs particle_pairs() yields:
+ * NONE = unfiltered candidates (src/cellgrid.rs:338-340), LT = `dsq < c*c` (benches/lj.rs:85),
+ * LE = `dsq <= c*c` (benches/cellgrid.rs:86, benches/iters.rs:74) */
+enum zb_cmp { ZB_CMP_NONE = 0, ZB_CMP_LT = 1, ZB_CMP_LE = 2 };
+
+enum zb_status {
+  ZB_OK = 0,
+  ZB_ERR_BAD_ARG = 1,
+  ZB_ERR_CUDA = 2,          /* CUDA runtime error; see zb_last_error */
+  ZB_ERR_CAPACITY = 3,      /* caller's output buffer too small; *n_out holds the needed size */
+  ZB_ERR_TOO_MANY = 4,      /* n > i32::MAX (src/cellgrid/flatindex.rs:87) */
+  ZB_ERR_GRID_TOO_LARGE = 5,/* bounding box / cutoff needs more cells than the engine can index */
+  ZB_ERR_NOT_BUILT = 6,
+  ZB_ERR_OUT_OF_WINDOW = 7  /* sharded rebuild: a particle lies outside the imposed box/slab */
+};
+
+/* GridInfo + Aabb (src/cellgrid/util.rs:19-27, 81-90) plus sizes. */
+typedef struct zb_info {
+  double inf[3];      /* Aabb::inf  -- GridInfo::origin() (util.rs:139-141) */
+  double sup[3];      /* Aabb::sup */
+  double cutoff;      /* GridInfo::cutoff() (util.rs:179-181) */
+  int32_t shape[3];   /* GridInfo::shape()   (util.rs:144-146) */
+  int32_t strides[3]; /* GridInfo::strides() (util.rs:149-151): 1, shape0+4, (shape0+4)(shape1+4) */
+  uint64_t n;         /* particles in the grid (FlatIndex.index.len()) */
+  uint64_t n_cells;   /* non-empty cells (cells.len(); CellGrid::iter().count(), iters.rs:261-266) */
+  int32_t ndim;
+  int32_t dtype;
+  int32_t keys_changed; /* FlatIndex::rebuild_mut's return value (flatindex.rs:140-152) for the
+                           last rebuild when key tracking is on, else -1 */
+  int32_t reserved;
+} zb_info;
+
+/* -- lifetime ------------------------------------------------------------------------------ */
+
+/* CellGrid::default() (src/cellgrid.rs:112): an empty grid with cutoff 1. ndim is 2 or 3. */
+int zb_grid_create(int dtype, int ndim, int device, zb_grid** out);
+void zb_grid_destroy(zb_grid* g);
+
+/* Stream all later calls on this handle are enqueued on (a cudaStream_t; NULL = legacy default
+ * stream).  A fresh handle owns a private non-blocking stream. */
+int zb_grid_set_stream(zb_grid* g, void* cuda_stream);
+
+/* Keep the previous per-particle keys so that zb_info.keys_changed reports what
+ * FlatIndex::rebuild_mut returns (flatindex.rs:113-153).  Off by default (costs one extra pass). */
+int zb_grid_track_key_changes(zb_grid* g, int enable);
+
+const char* zb_last_error(const zb_grid* g);
+
+/* -- construction -------------------------------------------------------------------------- */
+
+/* CellGrid::new / rebuild / rebuild_mut (src/cellgrid.rs:166-172, 187-238, 264-312).
+ * cutoff_or_null == NULL keeps the previous cutoff (Option<T>::None, flatindex.rs:118).
+ * Stages: Aabb::from_particles (util.rs:35-52) -> GridInfo::new (util.rs:191-220) ->
+ * flat_cell_index per particle (util.rs:291-297) -> counting sort into one contiguous,
+ * cell-sorted buffer (cellgrid.rs:196-231, storage.rs:77-81, 106-111). */
+int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutoff_or_null);
+
+/* Slab-sharded rebuild for multi-GPU runs (no counterpart upstream):
+ * the bounding box is IMPOSED (the all-reduced global Aabb) so every rank derives the same
+ * GridInfo and hence the same keys as a single-GPU grid; `xyz` holds this rank's particles of
+ * the z-layers [z_begin - 1, z_end) (home layers plus the lower halo layer, halo particles
+ * included by the caller); only cells of layers [z_begin, z_end) act as home cells, so every
+ * unordered pair is owned by exactly one rank.  labels_or_null gives the global label of each
+ * local particle (NULL: local order). */
+int zb_grid_rebuild_sharded(zb_grid* g, const void* xyz, uint64_t n, const uint32_t* labels_or_null,
+                            const double* cutoff_or_null, const double* inf, const double* sup,
+                            int64_t z_begin, int64_t z_end);
+
+/* Aabb::from_particles alone (util.rs:35-52): out[0..ndim) = inf, out[3..3+ndim) = sup as f64.
+ * Used by the sharded host to all-reduce the global box before zb_grid_rebuild_sharded. */
+int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6);
+
+/* Cell coordinate of every particle along one axis, floor((x[axis] - inf_axis) / cutoff) as i32 in
+ * the grid's dtype (the per-axis term of flat_cell_index, util.rs:294-296).  The sharded host uses
+ * it to assign particles to slabs and to pick the halo layer.  out: n int32 (host or device). */
+int zb_layer_of(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double cutoff, int axis,
+                int32_t* out);
+
+/* -- inspection ---------------------------------------------------------------------------- */
+
+/* CellGrid::info() (src/cellgrid.rs:346-348) */
+int zb_grid_info(zb_grid* g, zb_info* out);
+
+/* FlatIndex.index (flatindex.rs:19): the reference's flat cell key of every particle, in input
+ * order.  out: n int32 (host or device). */
+int zb_grid_keys(zb_grid* g, int32_t* out);
+
+/* FlatIndex::neighbor_indices (flatindex.rs:55-65): 3^ndim - 1 relative flat keys; the first
+ * half is the Half space (iters.rs:58-63).  out: room for 26 int32 (host). */
+int zb_grid_neighbor_indices(zb_grid* g, int32_t* out, int32_t* count);
+
+/* CellGrid::iter() (iters.rs:261-266): the non-empty cells, ascending key order: reference
+ * flat key, first slot in the cell-sorted buffer, particle count.  Host arrays of capacity cap. */
+int zb_grid_cells(zb_grid* g, int32_t* keys, uint32_t* begin, uint32_t* count, uint64_t cap,
+                  uint64_t* n_out);
+
+/* cell_storage() (src/cellgrid.rs:412-414): the cell-sorted buffer; labels: n uint32,
+ * xyz: packed [n][ndim] of the grid's dtype (host or device; either may be NULL). */
+int zb_grid_cell_storage(zb_grid* g, uint32_t* labels, void* xyz);
+
+/* -- pair enumeration and its consumers ---------------------------------------------------- */
+
+/* particle_pairs().filter(cmp).count() (src/cellgrid.rs:338-340 + benches/cellgrid.rs:84-88);
+ * par_particle_pairs (cellgrid.rs:447-451) is the same call: the enumeration is parallel over
+ * cells on the device.  filter_cutoff is squared in the grid's dtype (cutoff.powi(2)). */
+int zb_grid_pair_count(zb_grid* g, int cmp, double filter_cutoff, uint64_t* out);
+
+/* Materialised particle_pairs(): `ij` receives n_out rows (label_home, label_neighbor) of
+ * uint32 (interleaved; host or device).  Row order is unspecified, as upstream (iters.rs:251).
+ * If cap < needed: ZB_ERR_CAPACITY, *n_out = needed, nothing written. */
+int zb_grid_pairs(zb_grid* g, int cmp, double filter_cutoff, uint32_t* ij, uint64_t cap,
+                  uint64_t* n_out);
+
+/* Fused consumer of benches/lj.rs:42-47, 81-92: sum over kept pairs of 4*t*(t-1),
+ * t = (1/dsq)^3, accumulated hierarchically in f64.  energy: 1 double (host or device);
+ * n_pairs (optional, host or device): pairs kept. */
+int zb_grid_lj_energy(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs);
+
+/* -- point queries ------------------------------------------------- */
+
+/* CellGrid::query_neighbors for a batch (src/cellgrid.rs:360-401): for each of nq query points,
+ * the labels of all particles in the point's cell and its Full neighbourhood; with cmp != NONE
+ * filtered like the Python binding's `neighbors` (python/src/lib.rs:229-241).
+ * offsets: nq+1 uint64 (CSR over `labels`); a query outside the grid's one-cell margin
+ * (try_cell_index == None, util.rs:245-256) gets offsets[q+1]-offsets[q] == 0 and valid[q] = 0.
+ * If cap < needed: ZB_ERR_CAPACITY with *n_out = needed (offsets/valid are still written). */
+int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cmp,
+                            double filter_cutoff, uint64_t* offsets, uint8_t* valid,
+                            uint32_t* labels, uint64_t cap, uint64_t* n_out);
+
+/* -- introspection for benches -------------------------------------------------------------- */
+
+/* Number of kernel launches this handle has issued since creation (bench.py's gpu_launches). */
+uint64_t zb_grid_launch_count(const zb_grid* g);
+int zb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZELLL_B200_H */

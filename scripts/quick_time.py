@@ -1,0 +1,26 @@
+"""Ad-hoc timing of rebuild / pair_count / lj_energy with device-resident input (CUDA events)."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+import zelll_b200
+from zelll_b200 import workload
+
+def main():
+    n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
+    dtype = np.float32 if (len(sys.argv) > 2 and sys.argv[2] == "f32") else np.float64
+    pts = workload.generate_points_random(n, dtype=dtype)
+    t = torch.from_numpy(pts).cuda()
+    cg = zelll_b200.CellGrid(t, 10.0, dtype=dtype)
+    for name, fn in [("rebuild", lambda: cg.rebuild(t)), ("pair_count_le", lambda: cg.pair_count(10.0, "le")),
+                     ("lj_energy", lambda: cg.lj_energy(10.0, "lt")),
+                     ("rebuild+lj", lambda: (cg.rebuild(t), cg.lj_energy(10.0, "lt")))]:
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 10
+        for _ in range(reps): r = fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        print(f"{name:16s} n={n:.0e} {dtype.__name__}: {dt*1e3:8.3f} ms   result={r}")
+    print("info", cg.info().shape(), cg.info().n_cells)
+main()

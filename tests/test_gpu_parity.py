@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (zelll_b200.CellGrid is a ctypes
+shim over libzelll_b200.so), against the CPU oracle on the same seeded inputs, against the
+reference's known answers, and -- at BASELINE.json's full size -- through size-independent
+properties.  Bar: bit-exact for keys / cells / pair sets / counts; 1e-10 (f64) and 1e-5 (f32)
+relative for the Lennard-Jones energy."""
+import itertools
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import CMP_LE, CMP_LT, CMP_NONE, OracleCellGrid, canonical_pairs
+from zelll_b200 import workload
+
+pytestmark = pytest.mark.gpu
+
+F64_RTOL = 1e-10  # north_star tolerance, f64
+F32_RTOL = 1e-5   # north_star tolerance, f32
+OCMP = {"none": CMP_NONE, "lt": CMP_LT, "le": CMP_LE}
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import zelll_b200
+
+    return zelll_b200
+
+
+def _cloud(kind: str, n: int, dtype, ndim: int = 3, seed: int = 1):
+    rng = np.random.default_rng(seed)
+    if kind == "lj":  # the benchmark box (benches/lj.rs:59-66)
+        pts = workload.generate_points_random(n, dtype=dtype)
+        return pts[:, :ndim].copy(), 10.0
+    if kind == "cube":
+        side = max(1.0, (n / 4.0) ** (1.0 / ndim))
+        return (rng.random((n, ndim)) * side).astype(dtype), 1.0
+    if kind == "clusters":  # sparse: a few dense blobs far apart
+        centres = rng.random((6, ndim)) * 60.0
+        pts = centres[rng.integers(0, 6, n)] + rng.normal(0, 0.7, (n, ndim))
+        return pts.astype(dtype), 1.5
+    if kind == "plane":  # wide and flat: 2 layers in z
+        side = max(2.0, (n / 8.0) ** 0.5)
+        pts = rng.random((n, ndim)) * ([side, side, 2.0][:ndim])
+        return pts.astype(dtype), 1.0
+    if kind == "dense":  # few cells, many particles each (exceeds the shared-memory stage)
+        return (rng.random((n, ndim)) * 2.0).astype(dtype), 1.0
+    raise ValueError(kind)
+
+
+def _check_against_oracle(zb, pts, cutoff, dtype, ndim, cmps=("none", "lt", "le"), energy=True):
+    cg = zb.CellGrid(pts, cutoff, dtype=dtype, ndim=ndim)
+    og = OracleCellGrid(pts, cutoff, dtype=dtype, ndim=ndim)
+    info, oinfo = cg.info(), og.info()
+    assert info.origin().tolist() == oinfo["inf"]
+    assert info.bounding_box()[1].tolist() == oinfo["sup"]
+    assert info.shape().tolist() == oinfo["shape"]
+    assert info.strides().tolist() == oinfo["strides"]
+    assert info.n == oinfo["n"] == len(pts)
+    assert info.n_cells == oinfo["n_cells"]
+    # FlatIndex.index
+    assert np.array_equal(cg.keys(), og.keys())
+    assert cg.neighbor_indices().tolist() == og.neighbor_indices().tolist()
+    # cells: same key set, same sizes, same label multiset per cell (order inside a cell and of
+    # the cells in the buffer is unspecified upstream: hash-map order, iters.rs:262)
+    keys, begin, count = cg.cells()
+    okeys, obegin, olen = og.cells()
+    assert np.all(np.diff(keys) > 0)
+    order = np.argsort(okeys)
+    assert np.array_equal(keys, okeys[order])
+    assert np.array_equal(count.astype(np.uint64), olen[order])
+    labels, xyz = cg.cell_storage()
+    olabels, oxyz = og.cell_storage()
+    assert np.array_equal(xyz, np.asarray(pts, dtype=dtype)[labels])  # records carry their own coordinates
+    for k, (b, c) in enumerate(zip(begin, count)):
+        ob, oc = int(obegin[order[k]]), int(olen[order[k]])
+        assert sorted(labels[b:b + c].tolist()) == sorted(olabels[ob:ob + oc].tolist())
+        if k > 200:
+            break
+    # pair sets, bit-exact in canonical form
+    for cmp in cmps:
+        want = og.pairs_canonical(OCMP[cmp], cutoff)
+        got = canonical_pairs(cg.particle_pairs(cutoff, cmp))
+        assert got.shape == want.shape, (cmp, got.shape, want.shape)
+        assert np.array_equal(got, want), cmp
+        assert cg.pair_count(cutoff, cmp) == len(want)
+    if energy:
+        for cmp in ("lt", "le"):
+            e_t, e_64, npairs = og.lj_energy(OCMP[cmp], cutoff)
+            e, m = cg.lj_energy(cutoff, cmp, return_pairs=True)
+            assert m == npairs
+            rtol = F64_RTOL if np.dtype(dtype) == np.float64 else F32_RTOL
+            if np.isfinite(e_64):
+                assert abs(e - e_64) <= rtol * max(abs(e_64), 1e-300), (e, e_64)
+    return cg, og
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own known answers, on the GPU path
+def test_reference_utils_golden(zb, golden):
+    g = golden["test_utils"]
+    pts = oracle.generate_pointcloud(g["shape"], g["cutoff"], g["origin"])
+    cg = zb.CellGrid(pts, g["cutoff"])
+    info = cg.info()
+    assert info.origin().tolist() == g["aabb_inf"]
+    assert info.bounding_box()[1].tolist() == g["aabb_sup"]
+    assert cg.aabb() == (g["aabb_inf"], g["aabb_sup"])
+    assert info.shape().tolist() == g["grid_shape"]
+    assert info.strides().tolist() == g["grid_strides"]
+    for case in g["cell_index_cases"]:
+        assert info.try_cell_index(case["p"]) == case["cell"]
+        assert info.flat_cell_index(case["p"]) == case["flat"]
+        assert info.flatten_index(case["cell"]) == case["flat"]
+    # the device computes the same keys for these points (incl. the 1.9999999999999998 floor case)
+    probe = np.array([c["p"] for c in g["cell_index_cases"]])
+    cg2 = zb.CellGrid(np.vstack([pts, probe]), g["cutoff"])
+    assert cg2.keys()[len(pts):].tolist() == [c["flat"] for c in g["cell_index_cases"]]
+
+
+def test_reference_neighbor_indices_2d_golden(zb, golden):
+    g = golden["test_neighbor_indices_2d"]
+    cg = zb.CellGrid(np.array(g["points"]), g["cutoff"], ndim=2)
+    assert cg.neighbor_indices().tolist() == g["neighbor_indices"]
+
+
+def test_reference_flatindex_golden(zb, golden):
+    g = golden["test_flatindex"]
+    pts = oracle.generate_pointcloud(g["shape"], g["cutoff"], g["origin"])
+    cg = zb.CellGrid(pts, g["cutoff"])
+    info = cg.info()
+    want = []
+    for x, y, z in itertools.product(range(3), repeat=3):
+        if (x + y + z) % 2 == 0:
+            want += [info.flatten_index([x, y, z])] * 2
+    assert cg.keys().tolist() == want
+
+
+def test_reference_iter_counts_golden(zb, golden):
+    g = golden["test_cellgrid_iter"]
+    pts = oracle.generate_pointcloud(g["shape"], g["cutoff"], g["origin"])
+    cg = zb.CellGrid(pts, g["cutoff"])
+    keys, begin, count = cg.cells()
+    assert len(keys) == g["nonempty_cells"] == cg.info().n_cells
+    assert int(count.sum()) == len(pts)
+
+
+def test_reference_pair_counts_golden(zb, golden):
+    g = golden["test_neighborcell_particle_pairs"]
+    pts = oracle.generate_pointcloud(g["shape"], g["cutoff"], g["origin"])
+    cg = zb.CellGrid(pts, g["cutoff"])
+    assert cg.pair_count() == g["intra_half"] + g["inter_half"]
+    assert len(cg.particle_pairs()) == g["intra_half"] + g["inter_half"]
+    assert sum(1 for _ in cg) == g["intra_half"] + g["inter_half"]
+
+
+def test_reference_doctest_three_points(zb, golden):
+    g = golden["doctest_three_points"]
+    for dtype in (np.float32, np.float64):
+        _check_against_oracle(zb, np.array(g["points"], dtype=dtype), g["cutoff"], dtype, 3)
+        _check_against_oracle(zb, np.array(g["points_2d"], dtype=dtype), g["cutoff"], dtype, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded clouds vs the oracle
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,n", [("lj", 1000), ("lj", 20000), ("cube", 5000), ("clusters", 3000),
+                                    ("plane", 30000), ("dense", 6000)])
+def test_cloud_parity_3d(zb, kind, n, dtype):
+    pts, cutoff = _cloud(kind, n, dtype)
+    _check_against_oracle(zb, pts, cutoff, dtype, 3, energy=(kind != "dense" or dtype == np.float64))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,n", [("cube", 4000), ("clusters", 2000), ("dense", 3000)])
+def test_cloud_parity_2d(zb, kind, n, dtype):
+    pts, cutoff = _cloud(kind, n, dtype, ndim=2)
+    _check_against_oracle(zb, pts, cutoff, dtype, 2)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 257])
+def test_tiny_and_ragged_inputs(zb, n):
+    rng = np.random.default_rng(n)
+    pts = rng.random((n, 3)) * 3.0
+    _check_against_oracle(zb, pts, 1.0, np.float64, 3)
+
+
+def test_degenerate_clouds(zb):
+    same = np.zeros((40, 3)) + 0.25  # all particles coincide: dsq = 0, energy = inf
+    cg, og = _check_against_oracle(zb, same, 1.0, np.float64, 3, energy=False)
+    assert cg.pair_count(1.0, "le") == 40 * 39 // 2
+    assert cg.pair_count(1.0, "lt") == 40 * 39 // 2
+    line = np.zeros((500, 3))
+    line[:, 2] = np.linspace(0.0, 400.0, 500)  # shape [1, 1, 401]
+    _check_against_oracle(zb, line, 1.0, np.float64, 3)
+    # cutoff larger than the box: a single cell
+    _check_against_oracle(zb, np.random.default_rng(3).random((300, 3)), 5.0, np.float64, 3)
+    # negative coordinates / off-origin box
+    _check_against_oracle(zb, np.random.default_rng(4).random((2000, 3)) * 9.0 - 100.0, 1.0, np.float32, 3)
+
+
+def test_filter_radius_differs_from_grid_cutoff(zb):
+    pts, cutoff = _cloud("cube", 4000, np.float64)
+    cg = zb.CellGrid(pts, cutoff)
+    og = OracleCellGrid(pts, cutoff)
+    for r in (0.3, 0.77, 1.0):
+        assert np.array_equal(canonical_pairs(cg.particle_pairs(r, "le")), og.pairs_canonical(CMP_LE, r))
+
+
+def test_boundary_distances_lt_vs_le(zb):
+    # pairs exactly AT the cutoff: `<` drops them, `<=` keeps them (benches/lj.rs:85 vs cellgrid.rs:86)
+    pts = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.6, 0.8, 0.0], [3.0, 4.0, 0.0],
+                    [3.0, 4.0, 1.0]])
+    for dtype in (np.float32, np.float64):
+        cg, og = _check_against_oracle(zb, pts.astype(dtype), 1.0, dtype, 3)
+        assert cg.pair_count(1.0, "le") > cg.pair_count(1.0, "lt")
+
+
+# ---------------------------------------------------------------------------------------------
+# rebuild_mut: buffer reuse, cutoff = None, key-change flag
+def test_rebuild_mut_sequence(zb):
+    pts, cutoff = _cloud("lj", 5000, np.float64)
+    cg = zb.CellGrid(pts, cutoff)
+    og = OracleCellGrid(pts, cutoff)
+    cg.track_key_changes(True)
+    cg.rebuild(pts)  # primes the key history
+    for step in range(4):
+        amp = 0.0 if step == 1 else 0.3
+        pts = workload.perturb(pts, step, amp)
+        cg.rebuild_mut(pts, None)  # Option::None keeps the cutoff (flatindex.rs:118)
+        changed = og.rebuild_mut(pts, None)
+        assert cg.cutoff() == cutoff
+        assert cg.info().keys_changed == changed
+        assert np.array_equal(cg.keys(), og.keys())
+        assert np.array_equal(canonical_pairs(cg.particle_pairs(cutoff, "lt")), og.pairs_canonical(CMP_LT, cutoff))
+    # a new cutoff and a different particle count through the same handle
+    pts2, _ = _cloud("cube", 777, np.float64)
+    cg.rebuild(pts2, 0.5)
+    og2 = OracleCellGrid(pts2, 0.5)
+    assert cg.cutoff() == 0.5
+    assert np.array_equal(canonical_pairs(cg.particle_pairs(0.5, "le")), og2.pairs_canonical(CMP_LE, 0.5))
+
+
+def test_device_resident_input(zb):
+    import torch
+
+    pts, cutoff = _cloud("lj", 4000, np.float64)
+    t = torch.from_numpy(pts).cuda()
+    cg = zb.CellGrid(t, cutoff)
+    og = OracleCellGrid(pts, cutoff)
+    assert np.array_equal(cg.keys(), og.keys())
+    assert np.array_equal(canonical_pairs(cg.particle_pairs(cutoff, "lt")), og.pairs_canonical(CMP_LT, cutoff))
+
+
+# ---------------------------------------------------------------------------------------------
+# Python-binding behaviour (python/src/lib.rs)
+def test_python_binding_surface(zb):
+    pts = [[0.0, 0.0, 0.0], [1.0, 2.0, 0.0], "bogus", [0.0, 0.1, 0.2], [1.0, 2.0]]
+    cg = zb.CellGrid(pts, 1.0)  # unconvertible items are skipped but keep their index (lib.rs:47-57)
+    seen = sorted((min(i, j), max(i, j)) for (i, p), (j, q) in cg)
+    assert seen == [(0, 3)]
+    for (i, p), (j, q) in cg:
+        assert p == pts[i] and q == pts[j]
+    assert cg.cutoff() == 1.0
+    inf, sup = cg.aabb()
+    assert inf == [0.0, 0.0, 0.0] and sup == [1.0, 2.0, 0.2]
+    near = cg.neighbors([0.5, 1.0, 0.1])
+    assert near is not None
+    far = cg.query_neighbors([50.0, 50.0, 50.0])
+    assert far is None
+    empty = zb.CellGrid()
+    assert list(empty) == [] and empty.cutoff() == 1.0
+    clone = pickle.loads(pickle.dumps(cg))
+    assert sorted((min(i, j), max(i, j)) for (i, p), (j, q) in clone) == seen
+    it = iter(cg)
+    with pytest.raises(RuntimeError):
+        cg.rebuild(pts, 1.0)
+    del it
+    cg.rebuild(pts, 1.0)
+
+
+def test_query_neighbors_vs_oracle(zb):
+    pts, cutoff = _cloud("cube", 3000, np.float64)
+    cg = zb.CellGrid(pts, cutoff)
+    og = OracleCellGrid(pts, cutoff)
+    rng = np.random.default_rng(5)
+    lo, hi = pts.min(0) - 2.5 * cutoff, pts.max(0) + 2.5 * cutoff
+    queries = lo + rng.random((300, 3)) * (hi - lo)
+    queries[:20] = pts[:20]
+    for cmp in ("none", "le"):
+        offsets, valid, labels = cg.query_neighbors_batch(queries, cutoff, cmp)
+        for q in range(len(queries)):
+            want = og.query_neighbors(queries[q], OCMP[cmp], cutoff)
+            if want is None:
+                assert not valid[q] and offsets[q + 1] == offsets[q]
+            else:
+                assert valid[q]
+                got = labels[int(offsets[q]):int(offsets[q + 1])]
+                assert sorted(got.tolist()) == sorted(want.tolist())
+
+
+# ---------------------------------------------------------------------------------------------
+# slab-sharded grids, ranks emulated one after another on one GPU
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_union_equals_single_grid(zb, world):
+    from zelll_b200 import sharded
+
+    pts, cutoff = _cloud("lj", 20000, np.float64)
+    single = zb.CellGrid(pts, cutoff)
+    want = canonical_pairs(single.particle_pairs(cutoff, "lt"))
+    e_want, m_want = single.lj_energy(cutoff, "lt", return_pairs=True)
+    info = single.info()
+    inf, sup = info.bounding_box()
+    nz = int(info.shape()[2])
+    labels = np.arange(len(pts), dtype=np.uint32)
+    layer = np.floor((pts[:, 2] - inf[2]) / cutoff).astype(np.int64)
+    got, e_sum, m_sum = [], 0.0, 0
+    for r in range(world):
+        zb_, ze_ = sharded.slab_bounds(nz, world, r)
+        sel = (layer >= max(zb_ - 1, 0)) & (layer < ze_)
+        g = sharded.ShardedCellGrid(dtype=np.float64)
+        g.rebuild_local(pts[sel], labels[sel], cutoff, inf, sup, zb_, ze_)
+        got.append(g.particle_pairs(cutoff, "lt"))
+        e, m = g.lj_energy(cutoff, "lt", return_pairs=True)
+        e_sum += e
+        m_sum += m
+    got = canonical_pairs(np.concatenate(got))
+    assert np.array_equal(got, want)
+    assert m_sum == m_want
+    assert abs(e_sum - e_want) <= F64_RTOL * abs(e_want)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full size (n = 10^7): size-independent properties
+@pytest.mark.parametrize("dtype", [np.float64])
+def test_full_size_properties(zb, dtype):
+    n = 10_000_000
+    pts = workload.generate_points_random(n, dtype=dtype)
+    cg = zb.CellGrid(pts, 10.0, dtype=dtype)
+    info = cg.info()
+    assert info.shape().tolist() == [3, 3, (n + 89) // 90] or info.shape()[2] in ((n // 90), (n // 90) + 1, (n // 90) + 2)
+    keys, begin, count = cg.cells()
+    assert int(count.sum()) == n and np.all(np.diff(keys) > 0)
+    assert np.array_equal(begin, np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.uint32))
+    labels, xyz = cg.cell_storage()
+    assert np.array_equal(np.sort(labels), np.arange(n, dtype=np.uint32))  # a permutation
+    assert np.array_equal(xyz, pts[labels])
+    # every record sits in the cell its key names
+    k = cg.keys()
+    cell_of_slot = np.repeat(keys, count)
+    assert np.array_equal(k[labels], cell_of_slot)
+    # count == fused-consumer count == emitted rows; candidates >= filtered
+    c_le = cg.pair_count(10.0, "le")
+    c_lt = cg.pair_count(10.0, "lt")
+    e1, m1 = cg.lj_energy(10.0, "lt", return_pairs=True)
+    assert m1 == c_lt <= c_le <= cg.pair_count()
+    assert 15.5 * n < c_lt < 16.5 * n  # 16.0 in-cutoff pairs per particle
+    # a chunk of the oracle: the first 200k particles in z order form a closed sub-box
+    order = np.argsort(pts[:, 2], kind="stable")
+    sub = pts[order[:200_000]]
+    og = OracleCellGrid(sub, 10.0, dtype=dtype)
+    cs = zb.CellGrid(sub, 10.0, dtype=dtype)
+    e_o = og.lj_energy(CMP_LT, 10.0)
+    e_s, m_s = cs.lj_energy(10.0, "lt", return_pairs=True)
+    assert m_s == e_o[2]
+    assert abs(e_s - e_o[1]) <= F64_RTOL * abs(e_o[1])
+    # permutation invariance: same pair count, energy equal to reduction-order noise
+    perm = np.random.default_rng(0).permutation(n)
+    cg.rebuild(pts[perm])
+    e2, m2 = cg.lj_energy(10.0, "lt", return_pairs=True)
+    assert m2 == m1
+    assert abs(e2 - e1) <= F64_RTOL * abs(e1)
+    # idempotence of rebuild
+    cg.rebuild(pts[perm])
+    e3, m3 = cg.lj_energy(10.0, "lt", return_pairs=True)
+    assert (m3, e3) == (m2, e3) and abs(e3 - e2) <= 1e-13 * abs(e2)

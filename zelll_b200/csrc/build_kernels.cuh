@@ -1,0 +1,406 @@
+// build_kernels.cuh -- grid construction on the device (CellGrid::new / rebuild / rebuild_mut).
+//
+//   K1 bbox_kernel     Aabb::from_particles        (util.rs:35-52)
+//   K2 count_kernel    flat_cell_index + counting   (util.rs:291-297, cellgrid.rs:196-204)
+//   K3 scan_kernel     reserve_cell slice layout    (cellgrid.rs:207-209, storage.rs:106-111)
+//   K4 scatter_kernel  CellStorage::push            (cellgrid.rs:215-231, storage.rs:77-81)
+//
+// The reference's HashMap<i32, CellSliceMeta> is replaced by a dense uint32 table over the cell
+// box: counting uses one L2 atomic per particle, the single-pass decoupled look-back scan turns
+// counts into CSR offsets in place, and the scatter's fetch-add on the same table both ranks the
+// particle inside its cell and leaves table[c] = end of cell c.
+#pragma once
+
+#include "common.cuh"
+
+namespace zb {
+
+// ---------------------------------------------------------------------------------------------
+// K1: bounding box.  The packed [n][NDIM] array is read as a flat stream of 16-byte vectors
+// (fully coalesced); the grid stride is a multiple of NDIM vectors so every register slot of a
+// thread always sees the same axis.
+constexpr int kBboxThreads = 384;  // multiple of 2 and 3
+
+template <class T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  using type = float4;
+  static constexpr int n = 4;
+};
+template <>
+struct Vec16<double> {
+  using type = double2;
+  static constexpr int n = 2;
+};
+
+template <class T>
+__device__ __forceinline__ void vec_unpack(const float4& v, T* e) {
+  e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+}
+template <class T>
+__device__ __forceinline__ void vec_unpack(const double2& v, T* e) {
+  e[0] = v.x; e[1] = v.y;
+}
+
+// Streaming load that does not allocate in L1 (each input byte is used once per pass).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+template <class T>
+__device__ __forceinline__ T pos_inf();
+template <>
+__device__ __forceinline__ float pos_inf<float>() { return __int_as_float(0x7f800000); }
+template <>
+__device__ __forceinline__ double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000ll); }
+
+// partials: [gridDim.x][6] (min xyz, max xyz); out6: final (min xyz, max xyz).
+// VEC = elements per load: Vec16<T>::n when xyz is 16 B aligned, else 1.
+template <class T, int NDIM, int VEC>
+__global__ void __launch_bounds__(kBboxThreads) bbox_kernel(const T* __restrict__ xyz, uint64_t n,
+                                                            T* __restrict__ partials,
+                                                            unsigned* __restrict__ ticket,
+                                                            T* __restrict__ out6) {
+  const uint64_t total = n * NDIM;
+  const uint64_t nv = total / VEC;
+  const uint64_t S = (uint64_t)gridDim.x * blockDim.x;  // multiple of NDIM
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+  T mn[VEC], mx[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { mn[e] = pos_inf<T>(); mx[e] = -pos_inf<T>(); }
+
+  if constexpr (VEC > 1) {
+    using V = typename Vec16<T>::type;
+    const V* xv = reinterpret_cast<const V*>(xyz);
+    uint64_t v = t;
+    // 4 independent loads in flight per thread
+    for (; v + 3 * S < nv; v += 4 * S) {
+      V a = ld_stream(xv + v), b = ld_stream(xv + v + S), c = ld_stream(xv + v + 2 * S),
+        d = ld_stream(xv + v + 3 * S);
+      T ea[VEC], eb[VEC], ec[VEC], ed[VEC];
+      vec_unpack<T>(a, ea); vec_unpack<T>(b, eb); vec_unpack<T>(c, ec); vec_unpack<T>(d, ed);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        T lo = ea[e] < eb[e] ? ea[e] : eb[e];
+        T lo2 = ec[e] < ed[e] ? ec[e] : ed[e];
+        T hi = ea[e] > eb[e] ? ea[e] : eb[e];
+        T hi2 = ec[e] > ed[e] ? ec[e] : ed[e];
+        lo = lo < lo2 ? lo : lo2;
+        hi = hi > hi2 ? hi : hi2;
+        mn[e] = lo < mn[e] ? lo : mn[e];
+        mx[e] = hi > mx[e] ? hi : mx[e];
+      }
+    }
+    for (; v < nv; v += S) {
+      V a = ld_stream(xv + v);
+      T ea[VEC];
+      vec_unpack<T>(a, ea);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        mn[e] = ea[e] < mn[e] ? ea[e] : mn[e];
+        mx[e] = ea[e] > mx[e] ? ea[e] : mx[e];
+      }
+    }
+  } else {
+    for (uint64_t v = t; v < nv; v += S) {
+      T a = __ldg(xyz + v);
+      mn[0] = a < mn[0] ? a : mn[0];
+      mx[0] = a > mx[0] ? a : mx[0];
+    }
+  }
+
+  // fold the per-slot extrema onto axes: slot e of this thread always held axis (t*VEC+e) % NDIM
+  T cm[3] = {pos_inf<T>(), pos_inf<T>(), pos_inf<T>()};
+  T cM[3] = {-pos_inf<T>(), -pos_inf<T>(), -pos_inf<T>()};
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    int ax = (int)((t * VEC + e) % NDIM);
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d)
+      if (ax == d) {
+        cm[d] = mn[e] < cm[d] ? mn[e] : cm[d];
+        cM[d] = mx[e] > cM[d] ? mx[e] : cM[d];
+      }
+  }
+  // scalar tail (total % VEC elements), one element per thread of block 0
+  if (VEC > 1 && blockIdx.x == 0) {
+    uint64_t s = nv * VEC + threadIdx.x;
+    if (s < total) {
+      T a = __ldg(xyz + s);
+      int ax = (int)(s % NDIM);
+#pragma unroll
+      for (int d = 0; d < NDIM; ++d)
+        if (ax == d) {
+          cm[d] = a < cm[d] ? a : cm[d];
+          cM[d] = a > cM[d] ? a : cM[d];
+        }
+    }
+  }
+
+  auto fmin_ = [](T a, T b) { return a < b ? a : b; };
+  auto fmax_ = [](T a, T b) { return a > b ? a : b; };
+  __shared__ T s_red[kBboxThreads / 32][6];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    T a = warp_reduce(cm[d], fmin_);
+    T b = warp_reduce(cM[d], fmax_);
+    if (lane == 0) { s_red[warp][d] = a; s_red[warp][3 + d] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    T a = s_red[0][threadIdx.x];
+    for (int w = 1; w < kBboxThreads / 32; ++w)
+      a = threadIdx.x < 3 ? fmin_(a, s_red[w][threadIdx.x]) : fmax_(a, s_red[w][threadIdx.x]);
+    partials[(uint64_t)blockIdx.x * 6 + threadIdx.x] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  // last block: fold all partials (fixed order -> deterministic)
+  __threadfence();
+  T fm[3] = {pos_inf<T>(), pos_inf<T>(), pos_inf<T>()};
+  T fM[3] = {-pos_inf<T>(), -pos_inf<T>(), -pos_inf<T>()};
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    const volatile T* p = partials + (uint64_t)b * 6;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { fm[d] = fmin_(fm[d], p[d]); fM[d] = fmax_(fM[d], p[3 + d]); }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    T a = warp_reduce(fm[d], fmin_);
+    T b = warp_reduce(fM[d], fmax_);
+    if (lane == 0) { s_red[warp][d] = a; s_red[warp][3 + d] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    T a = s_red[0][threadIdx.x];
+    for (int w = 1; w < kBboxThreads / 32; ++w)
+      a = threadIdx.x < 3 ? fmin_(a, s_red[w][threadIdx.x]) : fmax_(a, s_red[w][threadIdx.x]);
+    out6[threadIdx.x] = a;
+    if (threadIdx.x == 0) *ticket = 0;  // re-arm for the next rebuild
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: per-particle cell id + histogram.  counts[c] += 1 with one no-return L2 atomic (RED).
+constexpr int kPointThreads = 256;
+
+template <class T, int NDIM>
+__global__ void __launch_bounds__(kPointThreads) count_kernel(const T* __restrict__ xyz, uint32_t n,
+                                                              GridParams<T> g,
+                                                              uint32_t* __restrict__ counts,
+                                                              int* __restrict__ flags) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T x, y, z;
+  load_point<T, NDIM>(xyz, i, x, y, z);
+  uint32_t c = local_cell(g, x, y, z);
+  if (c == 0xffffffffu) {
+    atomicOr(flags, 1);
+    return;
+  }
+  atomicAdd(counts + c, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: in-place exclusive scan of the count table, single pass with decoupled look-back.
+// state[tile] = (status << 32) | value ; status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(uint32_t* __restrict__ a, uint32_t m,
+                                                            unsigned long long* __restrict__ state,
+                                                            uint32_t* __restrict__ tile_counter,
+                                                            uint32_t* __restrict__ nonempty) {
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_prefix;
+  __shared__ uint32_t s_nonempty;
+  if (threadIdx.x == 0) {
+    s_tile = atomicAdd(tile_counter, 1u);
+    s_nonempty = 0;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  uint32_t v[kScanItems];
+  if (base + kScanItems <= m) {
+    const uint4* p = reinterpret_cast<const uint4*>(a + base);  // a is 16 B aligned, base % 16 == 0
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      uint4 q = p[k];
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v[k] = (base + k < m) ? a[base + k] : 0u;
+  }
+  uint32_t sum = 0, nz = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { sum += v[k]; nz += (v[k] != 0u); }
+
+  // block-wide exclusive scan of the thread sums
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  nz = warp_reduce(nz, [](uint32_t x, uint32_t y) { return x + y; });
+  if (lane == 31) s_warp[warp] = incl;
+  if (lane == 0 && nz) atomicAdd(&s_nonempty, nz);
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < kScanThreads / 32) ? s_warp[lane] : 0u;
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    if (lane < kScanThreads / 32) s_warp[lane] = wi - w;  // exclusive warp offsets
+    uint32_t aggregate = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
+
+    // decoupled look-back (warp 0)
+    uint32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_state(state, (2ull << 32) | aggregate);
+    } else {
+      if (lane == 0) st_state(state + tile, (1ull << 32) | aggregate);
+      int look = (int)tile - 1;
+      while (true) {
+        int idx = look - lane;
+        unsigned long long s = (idx >= 0) ? ld_state(state + idx) : (2ull << 32);
+        while (__any_sync(0xffffffffu, (s >> 32) == 0ull)) {
+          if ((s >> 32) == 0ull) s = ld_state(state + idx);
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+        int first = pm ? (__ffs(pm) - 1) : 32;
+        uint32_t val = (lane <= first) ? (uint32_t)(s & 0xffffffffull) : 0u;
+        val = warp_reduce(val, [](uint32_t x, uint32_t y) { return x + y; });
+        excl += val;
+        if (pm) break;
+        look -= 32;
+      }
+      if (lane == 0) st_state(state + tile, (2ull << 32) | (unsigned long long)(excl + aggregate));
+    }
+    if (lane == 0) s_prefix = excl;
+  }
+  __syncthreads();
+  uint32_t run = s_prefix + s_warp[warp] + (incl - sum);
+  if (base + kScanItems <= m) {
+    uint4* p = reinterpret_cast<uint4*>(a + base);
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      uint4 q;
+      q.x = run; run += v[4 * k];
+      q.y = run; run += v[4 * k + 1];
+      q.z = run; run += v[4 * k + 2];
+      q.w = run; run += v[4 * k + 3];
+      p[k] = q;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (base + k < m) a[base + k] = run;
+      run += v[k];
+    }
+  }
+  if (threadIdx.x == 0 && s_nonempty) atomicAdd(nonempty, s_nonempty);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: scatter.  pos = fetch-add(table[c]) ranks the particle inside its cell; the record goes
+// out as one aligned 16 B / 32 B write.  After this kernel table[c] == end of cell c.
+template <class T, int NDIM>
+__global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restrict__ xyz,
+                                                                const uint32_t* __restrict__ labels,
+                                                                uint32_t n, GridParams<T> g,
+                                                                uint32_t* __restrict__ cursor,
+                                                                Rec<T>* __restrict__ sorted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T x, y, z;
+  load_point<T, NDIM>(xyz, i, x, y, z);
+  uint32_t c = local_cell(g, x, y, z);
+  if (c == 0xffffffffu) return;  // flagged by count_kernel
+  uint32_t pos = atomicAdd(cursor + c, 1u);
+  store_rec(sorted + pos, x, y, z, labels ? __ldg(labels + i) : i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inspection helpers
+
+// FlatIndex.index in input order, recomputed from the cell-sorted records (same arithmetic as K2)
+template <class T>
+__global__ void keys_kernel(const Rec<T>* __restrict__ sorted, uint32_t n, GridParams<T> g,
+                            int32_t* __restrict__ out) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  Rec<T> r = load_rec(sorted + p);
+  out[r.label] = ref_key(g, r.x, r.y, r.z);
+}
+
+// FlatIndex::rebuild_mut's change detection (flatindex.rs:140-152): old keys beyond the old
+// length count as 0 (Vec::resize(size, 0), flatindex.rs:130)
+__global__ void keys_changed_kernel(const int32_t* __restrict__ old_keys, uint32_t n_old,
+                                    const int32_t* __restrict__ new_keys, uint32_t n,
+                                    int* __restrict__ changed) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t o = i < n_old ? old_keys[i] : 0;
+  if (o != new_keys[i]) *changed = 1;
+}
+
+// per-axis cell coordinate of packed input particles (slab assignment of the sharded host)
+template <class T>
+__global__ void layer_kernel(const T* __restrict__ xyz, uint32_t n, int ndim, int axis, T inf, T cutoff,
+                             int32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = cell_coord(__ldg(xyz + (uint64_t)i * ndim + axis), inf, cutoff);
+}
+
+// cell_storage(): unpack records into labels / packed coordinates
+template <class T, int NDIM>
+__global__ void unpack_kernel(const Rec<T>* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ labels,
+                              T* __restrict__ xyz) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  Rec<T> r = load_rec(sorted + p);
+  if (labels) labels[p] = r.label;
+  if (xyz) {
+    xyz[(uint64_t)p * NDIM] = r.x;
+    xyz[(uint64_t)p * NDIM + 1] = r.y;
+    if (NDIM == 3) xyz[(uint64_t)p * NDIM + 2] = r.z;
+  }
+}
+
+}  // namespace zb

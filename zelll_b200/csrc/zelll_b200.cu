@@ -1,0 +1,994 @@
+// zelll_b200.cu -- host side of the C ABI declared in include/zelll_b200.h (libzelll_b200.so).
+//
+// One translation unit: the kernels of build_kernels.cuh / pair_kernels.cuh / query_kernels.cuh
+// plus the handle that owns device memory, the stream and the launch sequence.  Compiled with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true
+// so that every floating-point operation is the separately rounded IEEE operation the Rust
+// reference performs ("bit-exact pair set").
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device zb_grid_create fails.
+#include "../../include/zelll_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "build_kernels.cuh"
+#include "pair_kernels.cuh"
+#include "query_kernels.cuh"
+
+using namespace zb;
+
+// ---------------------------------------------------------------------------------------------
+// handle
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+constexpr uint32_t kMaxBboxBlocks = 148 * 4;
+constexpr uint64_t kMaxDenseCells = (1ull << 31) - 16;  // uint32 cell ids, table of 4 B entries
+
+// small device scratch block, zeroed at creation; re-armed by the kernels / rebuild
+struct Misc {
+  unsigned ticket;         // bbox last-block ticket
+  uint32_t tile_counter;   // scan: dynamic tile ids
+  uint32_t nonempty;       // scan: non-empty cells
+  int flags;               // count: bit0 = particle outside the window
+  int keys_changed;        // keys_changed_kernel
+  int pad[3];
+  double out6[6];          // bbox result (T-typed, stored in the leading bytes)
+  double energy;           // finalize_kernel
+  unsigned long long pair_total;
+};
+
+}  // namespace
+
+struct zb_grid {
+  int device = 0;
+  int dtype = ZB_F64;
+  int ndim = 3;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  // grid state (reference: GridInfo + FlatIndex + cells + cell_lists)
+  bool built = false;
+  double cutoff = 1.0;          // value of T, widened
+  double inf[3] = {0, 0, 0};
+  double sup[3] = {0, 0, 0};
+  int shape[3] = {1, 1, 1};
+  int wlo[3] = {0, 0, 0};
+  int wshape[3] = {1, 1, 1};
+  uint64_t n = 0;
+  uint64_t n_cells_nonempty = 0;
+  uint32_t ncells = 1;          // stored (windowed) cells
+  uint32_t home_lo = 0, home_hi = 1;
+  bool sharded = false;
+  bool track_keys = false;
+  int keys_changed = -1;
+  uint64_t n_keys_old = 0;
+
+  // device memory, grown on demand and reused across rebuilds (rebuild_mut contract)
+  DevBuf in;        // staged input when the caller passes host memory
+  DevBuf labels_in; // staged labels (sharded, host labels)
+  DevBuf table;     // uint32 [4 + ncells + pad]; csr = table + 3, cursor = table + 4
+  DevBuf sorted;    // Rec<T>[n]
+  DevBuf scan_state;
+  DevBuf partials;  // bbox partials
+  DevBuf keys_old, keys_new;
+  DevBuf tile_counts, tile_offsets, block_energy, block_totals;
+  DevBuf out_stage; // staging for host-destination outputs
+  Misc* misc = nullptr;       // device
+  Misc* h_misc = nullptr;     // pinned host mirror for small read-backs
+  uint32_t pair_ntiles_cap = 0;
+};
+
+namespace {
+
+int fail(zb_grid* g, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (g) g->err = buf;
+  return code;
+}
+
+#define ZB_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(g, ZB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+#define ZB_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != ZB_OK) return rc__; \
+  } while (0)
+
+int reserve(zb_grid* g, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return ZB_OK;
+  if (b.p) {
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    ZB_CUDA(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = std::max<size_t>(bytes, 256);
+  ZB_CUDA(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return ZB_OK;
+}
+
+// 1 = device-accessible pointer, 0 = plain host memory
+int is_device_ptr(const void* p) {
+  if (!p) return 0;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+size_t elem_size(const zb_grid* g) { return g->dtype == ZB_F32 ? 4 : 8; }
+
+uint32_t* csr_ptr(zb_grid* g) { return static_cast<uint32_t*>(g->table.p) + 3; }
+uint32_t* cursor_ptr(zb_grid* g) { return static_cast<uint32_t*>(g->table.p) + 4; }
+
+template <class T>
+GridParams<T> make_params(const zb_grid* g) {
+  GridParams<T> p;
+  for (int d = 0; d < 3; ++d) {
+    p.inf[d] = (T)g->inf[d];
+    p.shape[d] = g->shape[d];
+    p.wlo[d] = g->wlo[d];
+    p.wshape[d] = g->wshape[d];
+  }
+  p.cutoff = (T)g->cutoff;
+  p.ndim = g->ndim;
+  p.ncells = g->ncells;
+  return p;
+}
+
+// copy `bytes` from device memory of the handle to a caller pointer (host or device)
+int deliver(zb_grid* g, void* dst, const void* dev_src, size_t bytes) {
+  if (!bytes) return ZB_OK;
+  if (is_device_ptr(dst)) {
+    ZB_CUDA(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToDevice, g->stream));
+  } else {
+    ZB_CUDA(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, g->stream));
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+  }
+  return ZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 launch: bounding box of a device array -> g->misc->out6 (as T)
+
+template <class T>
+int launch_bbox(zb_grid* g, const T* xyz, uint64_t n) {
+  const uint64_t total = n * (uint64_t)g->ndim;
+  constexpr int V = Vec16<T>::n;
+  const bool aligned = (reinterpret_cast<uintptr_t>(xyz) % 16) == 0;
+  const uint64_t per_block = (uint64_t)kBboxThreads * (aligned ? V : 1) * 4;
+  uint32_t blocks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((total + per_block - 1) / per_block, 1),
+                                                 std::min<uint64_t>((uint64_t)g->sm_count * 4, kMaxBboxBlocks));
+  ZB_TRY(reserve(g, g->partials, (size_t)kMaxBboxBlocks * 6 * sizeof(double)));
+  T* partials = static_cast<T*>(g->partials.p);
+  T* out6 = reinterpret_cast<T*>(g->misc->out6);
+  unsigned* ticket = &g->misc->ticket;
+  if (g->ndim == 3) {
+    if (aligned) bbox_kernel<T, 3, V><<<blocks, kBboxThreads, 0, g->stream>>>(xyz, n, partials, ticket, out6);
+    else bbox_kernel<T, 3, 1><<<blocks, kBboxThreads, 0, g->stream>>>(xyz, n, partials, ticket, out6);
+  } else {
+    if (aligned) bbox_kernel<T, 2, V><<<blocks, kBboxThreads, 0, g->stream>>>(xyz, n, partials, ticket, out6);
+    else bbox_kernel<T, 2, 1><<<blocks, kBboxThreads, 0, g->stream>>>(xyz, n, partials, ticket, out6);
+  }
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  return ZB_OK;
+}
+
+template <class T>
+int fetch_bbox(zb_grid* g, double* out6) {
+  ZB_CUDA(cudaMemcpyAsync(g->h_misc->out6, g->misc->out6, 6 * sizeof(T), cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  const T* t = reinterpret_cast<const T*>(g->h_misc->out6);
+  for (int d = 0; d < 6; ++d) out6[d] = (double)t[d];
+  return ZB_OK;
+}
+
+// GridInfo::new (util.rs:191-220), in the arithmetic of T
+template <class T>
+int derive_shape(zb_grid* g) {
+  const T c = (T)g->cutoff;
+  for (int d = 0; d < 3; ++d) g->shape[d] = 1;
+  for (int d = 0; d < g->ndim; ++d) {
+    const T q = std::floor(((T)g->sup[d] - (T)g->inf[d]) / c);
+    // Rust `as i32`: saturating, NaN -> 0; then `+ 1` (wrapping in release builds)
+    int s;
+    if (q != q) s = 0;
+    else if (q >= (T)2147483648.0) s = 2147483647;
+    else if (q <= (T)-2147483649.0) s = (-2147483647 - 1);
+    else s = (int)q;
+    if (s < 0 || s >= 2147483647 - 8)
+      return fail(g, ZB_ERR_GRID_TOO_LARGE, "axis %d needs %d cells (cutoff %g too small or not positive)", d, s,
+                  g->cutoff);
+    g->shape[d] = s + 1;
+  }
+  return ZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2..K4 launches: counting sort of `xyz` (device) into g->sorted / g->table
+
+template <class T>
+int build_sorted(zb_grid* g, const T* xyz, const uint32_t* labels, uint64_t n) {
+  // window -> stored cell count
+  uint64_t nc = 1;
+  for (int d = 0; d < 3; ++d) {
+    nc *= (uint64_t)g->wshape[d];
+    if (nc > kMaxDenseCells)
+      return fail(g, ZB_ERR_GRID_TOO_LARGE,
+                  "bounding box / cutoff needs more than 2^31 cells (%d x %d x %d): box too sparse for the "
+                  "dense cell table",
+                  g->wshape[0], g->wshape[1], g->wshape[2]);
+  }
+  g->ncells = (uint32_t)nc;
+  const size_t table_elems = 4 + (size_t)nc + kScanTile;  // slack so full-tile vector stores stay in bounds
+  size_t free_b = 0, total_b = 0;
+  if (table_elems * 4 > g->table.cap) {
+    ZB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (table_elems * 4 > free_b + g->table.cap)
+      return fail(g, ZB_ERR_GRID_TOO_LARGE, "dense cell table of %zu cells does not fit device memory", (size_t)nc);
+  }
+  ZB_TRY(reserve(g, g->table, table_elems * 4));
+  ZB_TRY(reserve(g, g->sorted, std::max<size_t>((size_t)n, 1) * sizeof(Rec<T>)));
+  const uint32_t ntile = (uint32_t)((nc + kScanTile - 1) / kScanTile);
+  ZB_TRY(reserve(g, g->scan_state, (size_t)ntile * sizeof(unsigned long long)));
+
+  // one memset clears the 4 leading entries (csr[0] = 0) and all counts
+  ZB_CUDA(cudaMemsetAsync(g->table.p, 0, (4 + (size_t)nc) * 4, g->stream));
+  ZB_CUDA(cudaMemsetAsync(g->scan_state.p, 0, (size_t)ntile * sizeof(unsigned long long), g->stream));
+  ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 3 * sizeof(uint32_t), g->stream));  // tile_counter, nonempty, flags
+
+  const GridParams<T> p = make_params<T>(g);
+  uint32_t* cursor = cursor_ptr(g);
+  if (n > 0) {
+    const uint32_t blocks = (uint32_t)((n + kPointThreads - 1) / kPointThreads);
+    if (g->ndim == 3)
+      count_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
+    else
+      count_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
+    g->launches++;
+  }
+  scan_kernel<<<ntile, kScanThreads, 0, g->stream>>>(cursor, (uint32_t)nc,
+                                                     static_cast<unsigned long long*>(g->scan_state.p),
+                                                     &g->misc->tile_counter, &g->misc->nonempty);
+  g->launches++;
+  if (n > 0) {
+    const uint32_t blocks = (uint32_t)((n + kPointThreads - 1) / kPointThreads);
+    Rec<T>* sorted = static_cast<Rec<T>*>(g->sorted.p);
+    if (g->ndim == 3)
+      scatter_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
+    else
+      scatter_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
+    g->launches++;
+  }
+  ZB_CUDA(cudaGetLastError());
+  return ZB_OK;
+}
+
+template <class T>
+int track_keys(zb_grid* g) {
+  // FlatIndex::rebuild_mut's return value (flatindex.rs:140-152)
+  const uint64_t n = g->n;
+  ZB_TRY(reserve(g, g->keys_new, std::max<uint64_t>(n, 1) * 4));
+  ZB_CUDA(cudaMemsetAsync(&g->misc->keys_changed, 0, sizeof(int), g->stream));
+  if (n) {
+    const uint32_t blocks = (uint32_t)((n + 255) / 256);
+    keys_kernel<T><<<blocks, 256, 0, g->stream>>>(static_cast<const Rec<T>*>(g->sorted.p), (uint32_t)n,
+                                                   make_params<T>(g), static_cast<int32_t*>(g->keys_new.p));
+    keys_changed_kernel<<<blocks, 256, 0, g->stream>>>(static_cast<const int32_t*>(g->keys_old.p),
+                                                       (uint32_t)g->n_keys_old,
+                                                       static_cast<const int32_t*>(g->keys_new.p), (uint32_t)n,
+                                                       &g->misc->keys_changed);
+    g->launches += 2;
+  }
+  ZB_CUDA(cudaGetLastError());
+  std::swap(g->keys_old, g->keys_new);
+  g->n_keys_old = n;
+  return ZB_OK;
+}
+
+// stage caller input on the device if it is host memory
+int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
+  const size_t bytes = (size_t)n * g->ndim * elem_size(g);
+  if (n == 0) {
+    *dev = nullptr;
+    return ZB_OK;
+  }
+  if (is_device_ptr(xyz)) {
+    *dev = xyz;
+    return ZB_OK;
+  }
+  ZB_TRY(reserve(g, g->in, bytes));
+  ZB_CUDA(cudaMemcpyAsync(g->in.p, xyz, bytes, cudaMemcpyHostToDevice, g->stream));
+  *dev = g->in.p;
+  return ZB_OK;
+}
+
+template <class T>
+int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* labels_any, const double* cutoff,
+                 const double* inf, const double* sup, int64_t z_begin, int64_t z_end, bool sharded) {
+  if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
+  if (n > 0 && !xyz_any) return fail(g, ZB_ERR_BAD_ARG, "xyz is NULL");
+  if (cutoff) {
+    const T c = (T)*cutoff;
+    if (!(c > (T)0) || !std::isfinite((double)c)) return fail(g, ZB_ERR_BAD_ARG, "cutoff must be positive and finite");
+    g->cutoff = (double)c;
+  }
+  g->built = false;
+  const void* dev = nullptr;
+  ZB_TRY(stage_input(g, xyz_any, n, &dev));
+  const T* xyz = static_cast<const T*>(dev);
+
+  const uint32_t* labels = nullptr;
+  if (labels_any && n) {
+    if (is_device_ptr(labels_any)) labels = labels_any;
+    else {
+      ZB_TRY(reserve(g, g->labels_in, n * 4));
+      ZB_CUDA(cudaMemcpyAsync(g->labels_in.p, labels_any, n * 4, cudaMemcpyHostToDevice, g->stream));
+      labels = static_cast<const uint32_t*>(g->labels_in.p);
+    }
+  }
+
+  if (!sharded) {
+    if (n == 0) {
+      // Aabb::from_particles on an empty iterator: zeros (util.rs:41)
+      for (int d = 0; d < 3; ++d) g->inf[d] = g->sup[d] = 0.0;
+    } else {
+      ZB_TRY(launch_bbox<T>(g, xyz, n));
+      double o[6];
+      ZB_TRY(fetch_bbox<T>(g, o));
+      for (int d = 0; d < 3; ++d) {
+        g->inf[d] = d < g->ndim ? o[d] : 0.0;
+        g->sup[d] = d < g->ndim ? o[3 + d] : 0.0;
+      }
+      for (int d = 0; d < g->ndim; ++d)
+        if (!std::isfinite(g->inf[d]) || !std::isfinite(g->sup[d]))
+          return fail(g, ZB_ERR_BAD_ARG, "non-finite coordinate on axis %d", d);
+    }
+  } else {
+    for (int d = 0; d < 3; ++d) {
+      g->inf[d] = d < g->ndim ? (double)(T)inf[d] : 0.0;
+      g->sup[d] = d < g->ndim ? (double)(T)sup[d] : 0.0;
+    }
+  }
+  ZB_TRY(derive_shape<T>(g));
+  for (int d = 0; d < 3; ++d) {
+    g->wlo[d] = 0;
+    g->wshape[d] = g->shape[d];
+  }
+  g->sharded = sharded;
+  if (sharded) {
+    const int ax = g->ndim - 1;  // slab axis = slowest (largest stride) axis
+    if (z_begin < 0 || z_end > g->shape[ax] || z_begin > z_end)
+      return fail(g, ZB_ERR_BAD_ARG, "slab [%lld, %lld) outside the %d layers of the grid", (long long)z_begin,
+                  (long long)z_end, g->shape[ax]);
+    const int lo = (int)std::max<int64_t>(z_begin - 1, 0);
+    g->wlo[ax] = lo;
+    g->wshape[ax] = std::max<int>((int)z_end - lo, 1);
+  }
+  ZB_TRY(build_sorted<T>(g, xyz, labels, n));
+
+  // home-cell range of the pair kernels
+  {
+    uint64_t plane = 1;
+    for (int d = 0; d < g->ndim - 1; ++d) plane *= (uint64_t)g->wshape[d];
+    if (sharded) {
+      const int ax = g->ndim - 1;
+      g->home_lo = (uint32_t)(plane * (uint64_t)(z_begin - g->wlo[ax]));
+      g->home_hi = (uint32_t)(plane * (uint64_t)(z_end - g->wlo[ax]));
+    } else {
+      g->home_lo = 0;
+      g->home_hi = g->ncells;
+    }
+  }
+  g->n = n;
+
+  // flags / non-empty count come back with the info read (one small sync copy)
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->tile_counter, &g->misc->tile_counter, 3 * sizeof(uint32_t),
+                          cudaMemcpyDeviceToHost, g->stream));
+  if (g->track_keys && !sharded) ZB_TRY(track_keys<T>(g));
+  if (g->track_keys && !sharded)
+    ZB_CUDA(cudaMemcpyAsync(&g->h_misc->keys_changed, &g->misc->keys_changed, sizeof(int), cudaMemcpyDeviceToHost,
+                            g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (g->h_misc->flags & 1)
+    return fail(g, sharded ? ZB_ERR_OUT_OF_WINDOW : ZB_ERR_BAD_ARG,
+                sharded ? "a particle lies outside the imposed box / slab window"
+                        : "a particle has a non-finite coordinate");
+  g->n_cells_nonempty = g->h_misc->nonempty;
+  g->keys_changed = (g->track_keys && !sharded) ? (g->h_misc->keys_changed ? 1 : 0) : -1;
+  g->built = true;
+  return ZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair kernels
+
+struct PairPlan {
+  uint32_t tile_cells, ntiles, stage_recs, blocks;
+  size_t smem;
+};
+
+template <class T>
+PairPlan plan_pairs(const zb_grid* g, size_t warp_smem) {
+  PairPlan pl;
+  pl.stage_recs = sizeof(T) == 8 ? 2048u : 4096u;  // 64 KB of records -> 3 CTAs per SM
+  const uint64_t plane = (g->ndim == 3) ? (uint64_t)g->wshape[0] * g->wshape[1] : 0;
+  const uint64_t halo = plane + (uint64_t)g->wshape[0] + 1;
+  const uint32_t nhome = g->home_hi - g->home_lo;
+  const double ppc = g->ncells ? (double)g->n / (double)g->ncells : 0.0;
+  uint32_t tc = 64;
+  if (halo + 1 + 8 < (uint64_t)kStageCells) {
+    // fill ~75 % of the stage with the expected load, bounded by the staged CSR window
+    const double budget = 0.75 * pl.stage_recs / std::max(ppc, 0.25);
+    const double room = std::min<double>(budget, (double)kStageCells - 1) - (double)halo;
+    if (room >= 8) tc = (uint32_t)room;
+  }
+  // enough tiles to balance the persistent grid
+  const uint32_t want_tiles = (uint32_t)g->sm_count * 3 * 4;
+  if (nhome / std::max(tc, 1u) < want_tiles) tc = std::max<uint32_t>(8, (nhome + want_tiles - 1) / want_tiles);
+  tc = std::max<uint32_t>(tc, 1);
+  pl.tile_cells = tc;
+  pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
+  pl.blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * 3));
+  pl.smem = (size_t)pl.stage_recs * sizeof(Rec<T>) + (kStageCells + 4) * sizeof(uint32_t) + kPairWarps * warp_smem;
+  return pl;
+}
+
+template <class T>
+PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) {
+  PairParams<T> p;
+  p.sorted = static_cast<const Rec<T>*>(g->sorted.p);
+  p.csr = csr_ptr(g);
+  p.w0 = g->wshape[0];
+  p.w1 = g->wshape[1];
+  p.w2 = g->wshape[2];
+  p.home_lo = g->home_lo;
+  p.home_hi = g->home_hi;
+  p.tile_cells = pl.tile_cells;
+  p.ntiles = pl.ntiles;
+  p.stage_recs = pl.stage_recs;
+  const T c = (T)filter_cutoff;
+  p.c2 = c * c;  // cutoff.powi(2) in T (benches/lj.rs:85)
+  return p;
+}
+
+template <class T, class Consumer>
+int launch_pairs(zb_grid* g, int cmp, const PairPlan& pl, const PairParams<T>& p, typename Consumer::Args args) {
+  auto go = [&](auto kern) -> int {
+    ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    kern<<<pl.blocks, kPairThreads, pl.smem, g->stream>>>(p, args);
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    return ZB_OK;
+  };
+  switch (cmp) {
+    case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer>);
+    case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer>);
+    case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer>);
+  }
+  return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+}
+
+int finalize(zb_grid* g, bool with_energy, uint32_t nblocks) {
+  finalize_kernel<<<1, 256, 0, g->stream>>>(with_energy ? static_cast<const double*>(g->block_energy.p) : nullptr,
+                                            static_cast<const unsigned long long*>(g->block_totals.p), nblocks,
+                                            &g->misc->energy, &g->misc->pair_total);
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  return ZB_OK;
+}
+
+template <class T>
+int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* plan_out) {
+  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes);
+  if (plan_out) *plan_out = pl;
+  ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
+  if (per_tile) ZB_TRY(reserve(g, g->tile_counts, ((size_t)pl.ntiles + 1) * 8));
+  typename CountConsumer<T>::Args a;
+  a.tile_counts = per_tile ? static_cast<unsigned long long*>(g->tile_counts.p) : nullptr;
+  a.block_totals = static_cast<unsigned long long*>(g->block_totals.p);
+  ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
+  if (pl.ntiles) ZB_TRY((launch_pairs<T, CountConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
+  ZB_TRY(finalize(g, false, pl.blocks));
+  return ZB_OK;
+}
+
+template <class T>
+int lj_impl(zb_grid* g, int cmp, double fc) {
+  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes);
+  ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
+  ZB_TRY(reserve(g, g->block_energy, (size_t)pl.blocks * 8));
+  typename LjConsumer<T>::Args a;
+  a.block_energy = static_cast<double*>(g->block_energy.p);
+  a.block_totals = static_cast<unsigned long long*>(g->block_totals.p);
+  ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
+  ZB_CUDA(cudaMemsetAsync(g->block_energy.p, 0, (size_t)pl.blocks * 8, g->stream));
+  if (pl.ntiles) ZB_TRY((launch_pairs<T, LjConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
+  ZB_TRY(finalize(g, true, pl.blocks));
+  return ZB_OK;
+}
+
+template <class T>
+int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev) {
+  tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), pl.ntiles,
+                                                 static_cast<unsigned long long*>(g->tile_offsets.p));
+  g->launches++;
+  typename EmitConsumer<T>::Args a;
+  a.tile_offsets = static_cast<const unsigned long long*>(g->tile_offsets.p);
+  a.out = out_dev;
+  PairPlan pe = pl;
+  pe.smem = (size_t)pl.stage_recs * sizeof(Rec<T>) + (kStageCells + 4) * sizeof(uint32_t) +
+            kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
+  if (pl.ntiles) ZB_TRY((launch_pairs<T, EmitConsumer<T>>(g, cmp, pe, pair_params<T>(g, pl, fc), a)));
+  return ZB_OK;
+}
+
+int check_built(zb_grid* g) {
+  if (!g) return ZB_ERR_BAD_ARG;
+  if (!g->built) return fail(g, ZB_ERR_NOT_BUILT, "grid has not been (successfully) built");
+  return ZB_OK;
+}
+
+int enter(zb_grid* g) {
+  if (!g) return ZB_ERR_BAD_ARG;
+  ZB_CUDA(cudaSetDevice(g->device));
+  return ZB_OK;
+}
+
+void free_buf(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+
+extern "C" {
+
+int zb_abi_version(void) { return ZB_ABI_VERSION; }
+
+int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
+  if (!out) return ZB_ERR_BAD_ARG;
+  *out = nullptr;
+  if ((dtype != ZB_F32 && dtype != ZB_F64) || (ndim != 2 && ndim != 3)) return ZB_ERR_BAD_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return ZB_ERR_CUDA;  // no CPU fallback
+  }
+  zb_grid* g = new (std::nothrow) zb_grid();
+  if (!g) return ZB_ERR_CUDA;
+  g->device = device;
+  g->dtype = dtype;
+  g->ndim = ndim;
+  auto bail = [&](int rc) {
+    zb_grid_destroy(g);
+    return rc;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(ZB_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(ZB_ERR_CUDA);
+  if (prop.major < 10) return bail(ZB_ERR_CUDA);  // sm_100a code only
+  g->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ZB_ERR_CUDA);
+  g->own_stream = true;
+  if (cudaMalloc(reinterpret_cast<void**>(&g->misc), sizeof(Misc)) != cudaSuccess) return bail(ZB_ERR_CUDA);
+  if (cudaMemset(g->misc, 0, sizeof(Misc)) != cudaSuccess) return bail(ZB_ERR_CUDA);
+  if (cudaMallocHost(reinterpret_cast<void**>(&g->h_misc), sizeof(Misc)) != cudaSuccess) return bail(ZB_ERR_CUDA);
+  memset(g->h_misc, 0, sizeof(Misc));
+  *out = g;
+  return ZB_OK;
+}
+
+void zb_grid_destroy(zb_grid* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
+                    &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
+                    &g->block_energy, &g->block_totals, &g->out_stage};
+  for (DevBuf* b : bufs) free_buf(*b);
+  if (g->misc) cudaFree(g->misc);
+  if (g->h_misc) cudaFreeHost(g->h_misc);
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  cudaGetLastError();
+  delete g;
+}
+
+int zb_grid_set_stream(zb_grid* g, void* cuda_stream) {
+  ZB_TRY(enter(g));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  g->stream = static_cast<cudaStream_t>(cuda_stream);
+  g->own_stream = false;
+  return ZB_OK;
+}
+
+int zb_grid_track_key_changes(zb_grid* g, int enable) {
+  if (!g) return ZB_ERR_BAD_ARG;
+  g->track_keys = enable != 0;
+  if (!g->track_keys) g->keys_changed = -1;
+  return ZB_OK;
+}
+
+const char* zb_last_error(const zb_grid* g) { return g ? g->err.c_str() : "null handle"; }
+
+int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutoff_or_null) {
+  ZB_TRY(enter(g));
+  return g->dtype == ZB_F32 ? rebuild_impl<float>(g, xyz, n, nullptr, cutoff_or_null, nullptr, nullptr, 0, 0, false)
+                            : rebuild_impl<double>(g, xyz, n, nullptr, cutoff_or_null, nullptr, nullptr, 0, 0, false);
+}
+
+int zb_grid_rebuild_sharded(zb_grid* g, const void* xyz, uint64_t n, const uint32_t* labels_or_null,
+                            const double* cutoff_or_null, const double* inf, const double* sup, int64_t z_begin,
+                            int64_t z_end) {
+  ZB_TRY(enter(g));
+  if (!inf || !sup) return fail(g, ZB_ERR_BAD_ARG, "inf / sup must be given");
+  return g->dtype == ZB_F32
+             ? rebuild_impl<float>(g, xyz, n, labels_or_null, cutoff_or_null, inf, sup, z_begin, z_end, true)
+             : rebuild_impl<double>(g, xyz, n, labels_or_null, cutoff_or_null, inf, sup, z_begin, z_end, true);
+}
+
+int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6) {
+  ZB_TRY(enter(g));
+  if (!out6) return fail(g, ZB_ERR_BAD_ARG, "out6 is NULL");
+  for (int d = 0; d < 6; ++d) out6[d] = 0.0;
+  if (n == 0) return ZB_OK;
+  if (!xyz) return fail(g, ZB_ERR_BAD_ARG, "xyz is NULL");
+  const void* dev = nullptr;
+  ZB_TRY(stage_input(g, xyz, n, &dev));
+  double o[6];
+  if (g->dtype == ZB_F32) {
+    ZB_TRY(launch_bbox<float>(g, static_cast<const float*>(dev), n));
+    ZB_TRY(fetch_bbox<float>(g, o));
+  } else {
+    ZB_TRY(launch_bbox<double>(g, static_cast<const double*>(dev), n));
+    ZB_TRY(fetch_bbox<double>(g, o));
+  }
+  for (int d = 0; d < g->ndim; ++d) {
+    out6[d] = o[d];
+    out6[3 + d] = o[3 + d];
+  }
+  return ZB_OK;
+}
+
+int zb_layer_of(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double cutoff, int axis, int32_t* out) {
+  ZB_TRY(enter(g));
+  if (axis < 0 || axis >= g->ndim) return fail(g, ZB_ERR_BAD_ARG, "bad axis %d", axis);
+  if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
+  if (n == 0) return ZB_OK;
+  if (!xyz || !out) return fail(g, ZB_ERR_BAD_ARG, "xyz / out is NULL");
+  const void* dev = nullptr;
+  ZB_TRY(stage_input(g, xyz, n, &dev));
+  const bool dev_out = is_device_ptr(out);
+  int32_t* dst = out;
+  if (!dev_out) {
+    ZB_TRY(reserve(g, g->out_stage, n * 4));
+    dst = static_cast<int32_t*>(g->out_stage.p);
+  }
+  const uint32_t blocks = (uint32_t)((n + 255) / 256);
+  if (g->dtype == ZB_F32)
+    layer_kernel<float><<<blocks, 256, 0, g->stream>>>(static_cast<const float*>(dev), (uint32_t)n, g->ndim, axis,
+                                                        (float)inf_axis, (float)cutoff, dst);
+  else
+    layer_kernel<double><<<blocks, 256, 0, g->stream>>>(static_cast<const double*>(dev), (uint32_t)n, g->ndim, axis,
+                                                         inf_axis, cutoff, dst);
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  if (!dev_out) ZB_TRY(deliver(g, out, dst, n * 4));
+  return ZB_OK;
+}
+
+int zb_grid_info(zb_grid* g, zb_info* out) {
+  if (!g || !out) return ZB_ERR_BAD_ARG;
+  memset(out, 0, sizeof *out);
+  for (int d = 0; d < 3; ++d) {
+    out->inf[d] = g->inf[d];
+    out->sup[d] = g->sup[d];
+    out->shape[d] = d < g->ndim ? g->shape[d] : 0;
+  }
+  // GridInfo strides (util.rs:200-212): wrapping i32 products of (shape + 4)
+  uint32_t s = 1;
+  for (int d = 0; d < 3; ++d) {
+    out->strides[d] = d < g->ndim ? (int32_t)s : 0;
+    s *= (uint32_t)(g->shape[d] + 4);
+  }
+  out->cutoff = g->cutoff;
+  out->n = g->n;
+  out->n_cells = g->n_cells_nonempty;
+  out->ndim = g->ndim;
+  out->dtype = g->dtype;
+  out->keys_changed = g->keys_changed;
+  return ZB_OK;
+}
+
+int zb_grid_keys(zb_grid* g, int32_t* out) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  if (g->sharded) return fail(g, ZB_ERR_BAD_ARG, "zb_grid_keys is not defined for sharded grids");
+  if (g->n == 0) return ZB_OK;
+  if (!out) return fail(g, ZB_ERR_BAD_ARG, "out is NULL");
+  const bool dev_out = is_device_ptr(out);
+  int32_t* dst = out;
+  if (!dev_out) {
+    ZB_TRY(reserve(g, g->out_stage, g->n * 4));
+    dst = static_cast<int32_t*>(g->out_stage.p);
+  }
+  const uint32_t blocks = (uint32_t)((g->n + 255) / 256);
+  if (g->dtype == ZB_F32)
+    keys_kernel<float><<<blocks, 256, 0, g->stream>>>(static_cast<const Rec<float>*>(g->sorted.p), (uint32_t)g->n,
+                                                       make_params<float>(g), dst);
+  else
+    keys_kernel<double><<<blocks, 256, 0, g->stream>>>(static_cast<const Rec<double>*>(g->sorted.p), (uint32_t)g->n,
+                                                        make_params<double>(g), dst);
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  if (!dev_out) ZB_TRY(deliver(g, out, dst, g->n * 4));
+  return ZB_OK;
+}
+
+int zb_grid_neighbor_indices(zb_grid* g, int32_t* out, int32_t* count) {
+  if (!g || !out || !count) return ZB_ERR_BAD_ARG;
+  // lexicographic product {-1,0,1}^N, last axis fastest, centre removed (flatindex.rs:55-65)
+  uint32_t strides[3];
+  uint32_t s = 1;
+  for (int d = 0; d < 3; ++d) {
+    strides[d] = s;
+    s *= (uint32_t)(g->shape[d] + 4);
+  }
+  int k = 0;
+  const int nd = g->ndim;
+  int total = 1;
+  for (int d = 0; d < nd; ++d) total *= 3;
+  for (int t = 0; t < total; ++t) {
+    int rem = t, off[3] = {0, 0, 0};
+    for (int d = nd - 1; d >= 0; --d) {
+      off[d] = rem % 3 - 1;
+      rem /= 3;
+    }
+    bool centre = true;
+    for (int d = 0; d < nd; ++d) centre = centre && off[d] == 0;
+    if (centre) continue;
+    uint32_t key = 0;
+    for (int d = 0; d < nd; ++d) key += (uint32_t)off[d] * strides[d];
+    out[k++] = (int32_t)key;
+  }
+  *count = k;
+  return ZB_OK;
+}
+
+int zb_grid_cells(zb_grid* g, int32_t* keys, uint32_t* begin, uint32_t* count, uint64_t cap, uint64_t* n_out) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  if (!n_out) return fail(g, ZB_ERR_BAD_ARG, "n_out is NULL");
+  *n_out = g->n_cells_nonempty;
+  if (cap < g->n_cells_nonempty) return fail(g, ZB_ERR_CAPACITY, "need room for %llu cells", (unsigned long long)*n_out);
+  if (g->n_cells_nonempty == 0) return ZB_OK;
+  // flags -> exclusive scan (K3's scan kernel) -> ordered compaction, then one copy per array
+  const uint64_t nc = g->n_cells_nonempty;
+  const uint32_t ntile = (g->ncells + kScanTile - 1) / kScanTile;
+  const size_t pos_elems = (size_t)ntile * kScanTile;
+  ZB_TRY(reserve(g, g->out_stage, pos_elems * 4 + nc * 12 + 64));
+  ZB_TRY(reserve(g, g->scan_state, (size_t)ntile * sizeof(unsigned long long)));
+  uint32_t* dpos = static_cast<uint32_t*>(g->out_stage.p);
+  int32_t* dk = reinterpret_cast<int32_t*>(dpos + pos_elems);
+  uint32_t* db = reinterpret_cast<uint32_t*>(dk + nc);
+  uint32_t* dc = db + nc;
+  ZB_CUDA(cudaMemsetAsync(g->scan_state.p, 0, (size_t)ntile * sizeof(unsigned long long), g->stream));
+  ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 2 * sizeof(uint32_t), g->stream));
+  const uint32_t blocks = (uint32_t)((g->ncells + 255) / 256);
+  cells_flag_kernel<<<blocks, 256, 0, g->stream>>>(csr_ptr(g), g->ncells, dpos);
+  scan_kernel<<<ntile, kScanThreads, 0, g->stream>>>(dpos, g->ncells, static_cast<unsigned long long*>(g->scan_state.p),
+                                                     &g->misc->tile_counter, &g->misc->nonempty);
+  cells_compact_kernel<<<blocks, 256, 0, g->stream>>>(csr_ptr(g), dpos, g->ncells, g->shape[0], g->shape[1], g->wlo[0],
+                                                     g->wlo[1], g->wlo[2], g->wshape[0], g->wshape[1], dk, db, dc);
+  g->launches += 3;
+  ZB_CUDA(cudaGetLastError());
+  if (keys) ZB_TRY(deliver(g, keys, dk, nc * 4));
+  if (begin) ZB_TRY(deliver(g, begin, db, nc * 4));
+  if (count) ZB_TRY(deliver(g, count, dc, nc * 4));
+  return ZB_OK;
+}
+
+int zb_grid_cell_storage(zb_grid* g, uint32_t* labels, void* xyz) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  const uint64_t n = g->n;
+  if (n == 0) return ZB_OK;
+  const size_t es = elem_size(g);
+  const bool ldev = labels && is_device_ptr(labels), xdev = xyz && is_device_ptr(xyz);
+  const size_t lbytes = n * 4, xbytes = n * g->ndim * es;
+  ZB_TRY(reserve(g, g->out_stage, lbytes + xbytes + 64));
+  uint32_t* dl = labels ? (ldev ? labels : static_cast<uint32_t*>(g->out_stage.p)) : nullptr;
+  void* dx = xyz ? (xdev ? xyz : static_cast<void*>(static_cast<char*>(g->out_stage.p) + ((lbytes + 15) / 16) * 16))
+                 : nullptr;
+  const uint32_t blocks = (uint32_t)((n + 255) / 256);
+  if (g->dtype == ZB_F32) {
+    auto* s = static_cast<const Rec<float>*>(g->sorted.p);
+    if (g->ndim == 3) unpack_kernel<float, 3><<<blocks, 256, 0, g->stream>>>(s, (uint32_t)n, dl, static_cast<float*>(dx));
+    else unpack_kernel<float, 2><<<blocks, 256, 0, g->stream>>>(s, (uint32_t)n, dl, static_cast<float*>(dx));
+  } else {
+    auto* s = static_cast<const Rec<double>*>(g->sorted.p);
+    if (g->ndim == 3) unpack_kernel<double, 3><<<blocks, 256, 0, g->stream>>>(s, (uint32_t)n, dl, static_cast<double*>(dx));
+    else unpack_kernel<double, 2><<<blocks, 256, 0, g->stream>>>(s, (uint32_t)n, dl, static_cast<double*>(dx));
+  }
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  if (labels && !ldev) ZB_TRY(deliver(g, labels, dl, lbytes));
+  if (xyz && !xdev) ZB_TRY(deliver(g, xyz, dx, xbytes));
+  return ZB_OK;
+}
+
+int zb_grid_pair_count(zb_grid* g, int cmp, double filter_cutoff, uint64_t* out) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  if (!out) return fail(g, ZB_ERR_BAD_ARG, "out is NULL");
+  if (cmp < 0 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+  if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff, false, nullptr));
+  else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff, false, nullptr));
+  return deliver(g, out, &g->misc->pair_total, 8);
+}
+
+int zb_grid_pairs(zb_grid* g, int cmp, double filter_cutoff, uint32_t* ij, uint64_t cap, uint64_t* n_out) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  if (!n_out) return fail(g, ZB_ERR_BAD_ARG, "n_out is NULL");
+  if (cmp < 0 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+  PairPlan pl;
+  if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff, true, &pl));
+  else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff, true, &pl));
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->pair_total, &g->misc->pair_total, 8, cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  const uint64_t total = g->h_misc->pair_total;
+  *n_out = total;
+  if (total > cap || (total && !ij))
+    return fail(g, ZB_ERR_CAPACITY, "pair list needs %llu rows, capacity is %llu", (unsigned long long)total,
+                (unsigned long long)cap);
+  if (total == 0) return ZB_OK;
+  const bool dev_out = is_device_ptr(ij);
+  uint2* dst = reinterpret_cast<uint2*>(ij);
+  if (!dev_out) {
+    ZB_TRY(reserve(g, g->out_stage, total * 8));
+    dst = static_cast<uint2*>(g->out_stage.p);
+  }
+  ZB_TRY(reserve(g, g->tile_offsets, ((size_t)pl.ntiles + 1) * 8));
+  if (g->dtype == ZB_F32) ZB_TRY(emit_impl<float>(g, cmp, filter_cutoff, pl, dst));
+  else ZB_TRY(emit_impl<double>(g, cmp, filter_cutoff, pl, dst));
+  if (!dev_out) ZB_TRY(deliver(g, ij, dst, total * 8));
+  return ZB_OK;
+}
+
+int zb_grid_lj_energy(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  if (!energy) return fail(g, ZB_ERR_BAD_ARG, "energy is NULL");
+  if (cmp < 1 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "lj energy needs a distance filter (cmp LT or LE)");
+  if (g->dtype == ZB_F32) ZB_TRY(lj_impl<float>(g, cmp, filter_cutoff));
+  else ZB_TRY(lj_impl<double>(g, cmp, filter_cutoff));
+  const bool edev = is_device_ptr(energy);
+  const bool pdev = n_pairs && is_device_ptr(n_pairs);
+  if (edev) ZB_CUDA(cudaMemcpyAsync(energy, &g->misc->energy, 8, cudaMemcpyDeviceToDevice, g->stream));
+  if (pdev) ZB_CUDA(cudaMemcpyAsync(n_pairs, &g->misc->pair_total, 8, cudaMemcpyDeviceToDevice, g->stream));
+  if (!edev || (n_pairs && !pdev)) {
+    ZB_CUDA(cudaMemcpyAsync(&g->h_misc->energy, &g->misc->energy, 16, cudaMemcpyDeviceToHost, g->stream));
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    if (!edev) *energy = g->h_misc->energy;
+    if (n_pairs && !pdev) *n_pairs = g->h_misc->pair_total;
+  }
+  return ZB_OK;
+}
+
+int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cmp, double filter_cutoff,
+                            uint64_t* offsets, uint8_t* valid, uint32_t* labels, uint64_t cap, uint64_t* n_out) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  if (!offsets || !n_out) return fail(g, ZB_ERR_BAD_ARG, "offsets / n_out is NULL");
+  if (cmp < 0 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+  if (g->sharded) return fail(g, ZB_ERR_BAD_ARG, "point queries are not defined for sharded grids");
+  if (nq > 0xffffffffull) return fail(g, ZB_ERR_TOO_MANY, "too many queries");
+  *n_out = 0;
+  if (nq == 0) {
+    if (is_device_ptr(offsets)) ZB_CUDA(cudaMemsetAsync(offsets, 0, 8, g->stream));
+    else offsets[0] = 0;
+    return ZB_OK;
+  }
+  if (!queries) return fail(g, ZB_ERR_BAD_ARG, "queries is NULL");
+  const size_t es = elem_size(g);
+  const size_t qbytes = nq * g->ndim * es;
+  // device scratch: [queries (if host)] [counts u64 nq+1] [valid u8 nq]
+  const bool qdev = is_device_ptr(queries);
+  ZB_TRY(reserve(g, g->in, qdev ? 256 : qbytes));  // reuse the input stage (grid data lives in `sorted`)
+  const void* dq = queries;
+  if (!qdev) {
+    ZB_CUDA(cudaMemcpyAsync(g->in.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
+    dq = g->in.p;
+  }
+  ZB_TRY(reserve(g, g->tile_offsets, (nq + 1) * 8 + nq + 64));
+  unsigned long long* doff = static_cast<unsigned long long*>(g->tile_offsets.p);
+  uint8_t* dvalid = reinterpret_cast<uint8_t*>(doff + nq + 1);
+  const uint32_t wblocks = (uint32_t)((nq * 32 + 255) / 256);
+  auto run = [&](auto tag, bool emit, uint32_t* dl) -> int {
+    using T = decltype(tag);
+    QueryParams<T> qp;
+    qp.g = make_params<T>(g);
+    qp.sorted = static_cast<const Rec<T>*>(g->sorted.p);
+    qp.csr = csr_ptr(g);
+    const T c = (T)filter_cutoff;
+    qp.c2 = c * c;
+    qp.cmp = cmp;
+    const T* q = static_cast<const T*>(dq);
+    if (!emit) query_kernel<T, false><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, nullptr);
+    else query_kernel<T, true><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, dl);
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    return ZB_OK;
+  };
+  // pass 1: counts -> exclusive scan -> offsets
+  if (g->dtype == ZB_F32) ZB_TRY(run(float(), false, nullptr));
+  else ZB_TRY(run(double(), false, nullptr));
+  ZB_TRY(reserve(g, g->tile_counts, (nq + 1) * 8));
+  ZB_CUDA(cudaMemcpyAsync(g->tile_counts.p, doff, nq * 8, cudaMemcpyDeviceToDevice, g->stream));
+  tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), (uint32_t)nq,
+                                                 doff);
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->pair_total, doff + nq, 8, cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  const uint64_t total = g->h_misc->pair_total;
+  *n_out = total;
+  ZB_TRY(deliver(g, offsets, doff, (nq + 1) * 8));
+  if (valid) ZB_TRY(deliver(g, valid, dvalid, nq));
+  if (total > cap || (total && !labels))
+    return fail(g, ZB_ERR_CAPACITY, "neighbour list needs %llu entries, capacity is %llu", (unsigned long long)total,
+                (unsigned long long)cap);
+  if (total == 0) return ZB_OK;
+  const bool ldev = is_device_ptr(labels);
+  uint32_t* dl = labels;
+  if (!ldev) {
+    ZB_TRY(reserve(g, g->out_stage, total * 4));
+    dl = static_cast<uint32_t*>(g->out_stage.p);
+  }
+  if (g->dtype == ZB_F32) ZB_TRY(run(float(), true, dl));
+  else ZB_TRY(run(double(), true, dl));
+  if (!ldev) ZB_TRY(deliver(g, labels, dl, total * 4));
+  return ZB_OK;
+}
+
+uint64_t zb_grid_launch_count(const zb_grid* g) { return g ? g->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Slab-decomposed CellGrid across the GPUs of one node.
+
+The reference has nothing distributed (its only parallelism is rayon over cells,
+src/cellgrid/iters.rs:282-290); this is new work behind the same API.  One process per GPU:
+
+1. local `Aabb::from_particles` (util.rs:35-52) then all-reduce(min, max): every rank derives the
+   SAME GridInfo (util.rs:191-220), hence the same keys and the same pair set as one big grid;
+2. z-layers (the slowest axis, largest stride: util.rs:200-212) are split into `world` slabs;
+3. one all-to-all-v routes each particle to the rank owning its layer AND to the rank whose lower
+   halo layer it is (the z-major half shell only looks at layers z-1 and z); slab-local input
+   (presorted or generated per slab) only moves its top layer: a single send/recv over NVLink;
+4. each unordered pair is owned by the rank owning its home cell -- no double counting;
+5. all-reduce(sum) of the f64 energy and of the pair count.  Pair lists stay sharded.
+
+`ShardedCellGrid` is the per-rank engine (zb_grid_rebuild_sharded); `DistributedCellGrid` is the
+torch.distributed orchestration and takes the engine as a parameter so its routing logic is
+testable on CPU (gloo) without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi
+from .cellgrid import CMP, CellGrid, _is_torch
+
+
+def slab_bounds(n_layers: int, world: int, rank: int):
+    """Layers [begin, end) owned by `rank`: equal layer counts (the benchmark box is uniform)."""
+    return (rank * n_layers) // world, ((rank + 1) * n_layers) // world
+
+
+def grid_shape(inf, sup, cutoff, dtype) -> list:
+    """`GridInfo::new` shape (util.rs:198) in the arithmetic of `dtype`."""
+    T = np.dtype(dtype).type
+    inf = np.asarray(inf, dtype=dtype)
+    sup = np.asarray(sup, dtype=dtype)
+    return [int(np.floor((s - i) / T(cutoff))) + 1 for i, s in zip(inf, sup)]
+
+
+class ShardedCellGrid(CellGrid):
+    """One rank's slab: home layers [z_begin, z_end) plus the lower halo layer."""
+
+    def __init__(self, *, dtype=np.float64, ndim: int = 3, device: int = 0, cutoff: float = 1.0):
+        super().__init__(None, cutoff, dtype=dtype, ndim=ndim, device=device)
+        self._keep = None
+
+    # -- engine interface used by DistributedCellGrid ---------------------------------------
+    def local_aabb(self, points):
+        ptr, n, keep, _ = self._marshal(points)
+        out = (C.c_double * 6)()
+        self._check(self._lib.zb_aabb(self._h, ptr, n, out))
+        nd = self.ndim
+        if n == 0:
+            return np.full(nd, np.inf), np.full(nd, -np.inf)
+        return np.array(out[0:nd]), np.array(out[3:3 + nd])
+
+    def layer_of(self, points, inf_axis: float, cutoff: float, axis: Optional[int] = None):
+        axis = self.ndim - 1 if axis is None else axis
+        ptr, n, keep, _ = self._marshal(points)
+        if _is_torch(points) and points.is_cuda:
+            import torch
+
+            out = torch.empty(n, dtype=torch.int32, device=points.device)
+            self._check(self._lib.zb_layer_of(self._h, ptr, n, float(inf_axis), float(cutoff), axis, out.data_ptr()))
+            return out
+        out = np.empty(n, dtype=np.int32)
+        self._check(self._lib.zb_layer_of(self._h, ptr, n, float(inf_axis), float(cutoff), axis, out.ctypes.data))
+        if _is_torch(points):
+            import torch
+
+            return torch.from_numpy(out)
+        return out
+
+    def rebuild_local(self, points, labels, cutoff, inf, sup, z_begin: int, z_end: int) -> None:
+        ptr, n, keep, _ = self._marshal(points)
+        lab_keep, lptr = None, None
+        if labels is not None:
+            if _is_torch(labels):
+                import torch
+
+                lab_keep = labels.to(torch.int32).contiguous() if labels.dtype not in (torch.int32, torch.uint32) else labels.contiguous()
+                lptr = lab_keep.data_ptr()
+            else:
+                lab_keep = np.ascontiguousarray(labels, dtype=np.uint32)
+                lptr = lab_keep.ctypes.data
+        a_inf = (C.c_double * 3)(*([float(v) for v in inf] + [0.0] * (3 - len(inf))))
+        a_sup = (C.c_double * 3)(*([float(v) for v in sup] + [0.0] * (3 - len(sup))))
+        self._check(self._lib.zb_grid_rebuild_sharded(self._h, ptr, n, lptr, self._optional(cutoff), a_inf, a_sup,
+                                                      int(z_begin), int(z_end)))
+        self._points, self._label_map, self._keep = keep, None, lab_keep
+        if cutoff is not None:
+            self._cutoff = float(self.dtype.type(cutoff))
+
+
+class DistributedCellGrid:
+    """torch.distributed orchestration of one ShardedCellGrid per rank."""
+
+    def __init__(self, engine=None, *, dtype=np.float64, ndim: int = 3, device: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.dtype = np.dtype(dtype)
+        self.ndim = ndim
+        self.backend = dist.get_backend(group)
+        if engine is None:
+            engine = ShardedCellGrid(dtype=dtype, ndim=ndim, device=0 if device is None else device)
+        self.engine = engine
+        self.comm_device = torch.device("cuda", 0 if device is None else device) if self.backend == "nccl" else torch.device("cpu")
+        self.inf = self.sup = None
+        self.shape = None
+        self.cutoff = None
+        self.z_begin = self.z_end = 0
+        self.n_home = 0
+        self.n_halo = 0
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _tdtype(self):
+        return self._torch.float32 if self.dtype == np.float32 else self._torch.float64
+
+    def _global_box(self, points, cutoff):
+        torch, dist = self._torch, self._dist
+        lo, hi = self.engine.local_aabb(points)
+        buf = torch.tensor(np.concatenate([-np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)]),
+                           dtype=torch.float64, device=self.comm_device)
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)  # max(-inf_d) = -min(inf_d)
+        buf = buf.cpu().numpy()
+        nd = self.ndim
+        inf, sup = -buf[:nd], buf[nd:]
+        if not np.all(np.isfinite(inf)):  # no particles anywhere: Aabb of an empty set is zeros (util.rs:41)
+            inf, sup = np.zeros(nd), np.zeros(nd)
+        self.inf, self.sup, self.cutoff = inf, sup, float(self.dtype.type(cutoff))
+        self.shape = grid_shape(inf, sup, cutoff, self.dtype)
+        self.z_begin, self.z_end = slab_bounds(self.shape[-1], self.world, self.rank)
+
+    def _bounds(self):
+        nz = self.shape[-1]
+        return [slab_bounds(nz, self.world, r) for r in range(self.world)]
+
+    # -- construction ------------------------------------------------------------------------------
+    def rebuild(self, points, cutoff: float, labels=None, label_offset: int = 0):
+        """General input: every rank holds an arbitrary subset of the particles (torch tensor on the
+        communication device).  `labels` (or label_offset + local index) are the global labels."""
+        torch, dist = self._torch, self._dist
+        points = points.reshape(-1, self.ndim).to(self._tdtype()).contiguous()
+        n = points.shape[0]
+        if labels is None:
+            labels = torch.arange(label_offset, label_offset + n, dtype=torch.int64, device=points.device)
+        labels = labels.to(torch.int64)
+        self._global_box(points, cutoff)
+        layer = self.engine.layer_of(points, float(self.inf[-1]), self.cutoff)
+        layer = torch.as_tensor(layer).to(points.device).to(torch.int64)
+        # destination lists: rank q receives its home layers and its lower halo layer
+        send_idx, counts = [], []
+        for (zb_, ze_) in self._bounds():
+            if ze_ <= zb_:
+                sel = torch.zeros(0, dtype=torch.int64, device=points.device)
+            else:
+                sel = torch.nonzero((layer >= zb_ - 1) & (layer < ze_)).reshape(-1)
+            send_idx.append(sel)
+            counts.append(int(sel.numel()))
+        order = torch.cat(send_idx) if send_idx else torch.zeros(0, dtype=torch.int64)
+        send_pts = points[order].contiguous()
+        send_lab = labels[order].contiguous()
+        cnt = torch.tensor(counts, dtype=torch.int64, device=self.comm_device)
+        rcnt = torch.empty_like(cnt)
+        dist.all_to_all_single(rcnt, cnt, group=self.group)
+        rcounts = [int(v) for v in rcnt.cpu().tolist()]
+        recv_pts = torch.empty((sum(rcounts), self.ndim), dtype=points.dtype, device=points.device)
+        recv_lab = torch.empty(sum(rcounts), dtype=torch.int64, device=points.device)
+        dist.all_to_all_single(recv_pts, send_pts, output_split_sizes=rcounts, input_split_sizes=counts, group=self.group)
+        dist.all_to_all_single(recv_lab, send_lab, output_split_sizes=rcounts, input_split_sizes=counts, group=self.group)
+        self._finish(recv_pts, recv_lab)
+
+    def rebuild_slab_local(self, buf, n_local: int, cutoff: float, label_offset: int, box=None):
+        """Fast path: rank r already holds exactly the particles of its own layers in buf[:n_local]
+        (generated per slab, or presorted and split at layer boundaries); buf has spare rows at the
+        tail that receive the lower halo layer from rank r-1 -- the only NVLink traffic.
+        `box` = (inf, sup) skips the bounding-box all-reduce when the global box is known."""
+        torch, dist = self._torch, self._dist
+        points = buf[:n_local]
+        if box is None:
+            self._global_box(points, cutoff)
+        else:
+            self.inf, self.sup = np.asarray(box[0], dtype=np.float64), np.asarray(box[1], dtype=np.float64)
+            self.cutoff = float(self.dtype.type(cutoff))
+            self.shape = grid_shape(self.inf, self.sup, cutoff, self.dtype)
+            self.z_begin, self.z_end = slab_bounds(self.shape[-1], self.world, self.rank)
+        layer = torch.as_tensor(self.engine.layer_of(points, float(self.inf[-1]), self.cutoff)).to(points.device)
+        if n_local and (int(layer.min()) < self.z_begin or int(layer.max()) >= self.z_end):
+            raise ValueError("rebuild_slab_local: input is not slab-local; use rebuild()")
+        top = torch.nonzero(layer == self.z_end - 1).reshape(-1)
+        up, down = self.rank + 1, self.rank - 1
+        n_send = torch.tensor([int(top.numel())], dtype=torch.int64, device=self.comm_device)
+        n_recv = torch.zeros(1, dtype=torch.int64, device=self.comm_device)
+        ops = []
+        if up < self.world:
+            ops.append(dist.P2POp(dist.isend, n_send, up, group=self.group))
+        if down >= 0:
+            ops.append(dist.P2POp(dist.irecv, n_recv, down, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        n_halo = int(n_recv.item())
+        if n_local + n_halo > buf.shape[0]:
+            raise ValueError(f"halo of {n_halo} rows does not fit the {buf.shape[0] - n_local} spare rows of buf")
+        send_pts = points[top].contiguous()
+        send_lab = (top + label_offset).to(torch.int64)
+        recv_lab = torch.empty(n_halo, dtype=torch.int64, device=points.device)
+        ops = []
+        if up < self.world and top.numel():
+            ops += [dist.P2POp(dist.isend, send_pts, up, group=self.group),
+                    dist.P2POp(dist.isend, send_lab, up, group=self.group)]
+        if down >= 0 and n_halo:
+            ops += [dist.P2POp(dist.irecv, buf[n_local:n_local + n_halo], down, group=self.group),
+                    dist.P2POp(dist.irecv, recv_lab, down, group=self.group)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        labels = torch.cat([torch.arange(label_offset, label_offset + n_local, dtype=torch.int64, device=points.device),
+                            recv_lab])
+        self._finish(buf[:n_local + n_halo], labels)
+
+    def _finish(self, pts, labels):
+        torch = self._torch
+        self.n_total_local = int(pts.shape[0])
+        lab32 = labels.to(torch.int64).cpu().numpy().astype(np.uint32) if not pts.is_cuda else labels.to(torch.int32)
+        # int64 -> int32 keeps the low 32 bits: labels are u32 on the device
+        self.engine.rebuild_local(pts, lab32, self.cutoff, self.inf, self.sup, self.z_begin, self.z_end)
+
+    # -- consumers -----------------------------------------------------------------------------------
+    def _allreduce_sum(self, values, dtype):
+        torch, dist = self._torch, self._dist
+        t = torch.tensor(values, dtype=dtype, device=self.comm_device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().tolist()
+
+    def pair_count(self, cutoff: Optional[float] = None, cmp="none") -> int:
+        local = self.engine.pair_count(self.cutoff if cutoff is None else cutoff, cmp)
+        return int(self._allreduce_sum([local], self._torch.int64)[0])
+
+    def lj_energy(self, cutoff: Optional[float] = None, cmp="lt", return_pairs: bool = False):
+        e, m = self.engine.lj_energy(self.cutoff if cutoff is None else cutoff, cmp, return_pairs=True)
+        e_all = self._allreduce_sum([e], self._torch.float64)[0]
+        if not return_pairs:
+            return e_all
+        return e_all, int(self._allreduce_sum([m], self._torch.int64)[0])
+
+    def local_particle_pairs(self, cutoff: Optional[float] = None, cmp="none") -> np.ndarray:
+        """This rank's shard of the pair list (global labels); the list stays sharded."""
+        return self.engine.particle_pairs(self.cutoff if cutoff is None else cutoff, cmp)
