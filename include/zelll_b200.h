@@ -170,6 +170,24 @@ int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cm
 
 /* -- introspection for benches -------------------------------------------------------------- */
 
+/* Per-stage device time of the hot launches, measured with cudaEvent pairs on the handle's stream
+ * (bench.py's roofline numbers).  zb_grid_profile(g, 1) clears the accumulators and turns recording
+ * on; zb_grid_profile_read synchronises the stream and returns, per stage, the summed milliseconds
+ * and the number of launches since then (arrays of ZB_NSTAGES). */
+enum zb_stage {
+  ZB_STAGE_BBOX = 0,       /* K1 Aabb::from_particles */
+  ZB_STAGE_COUNT = 1,      /* K2 cell keys + histogram */
+  ZB_STAGE_SCAN = 2,       /* K3 counts -> CSR offsets */
+  ZB_STAGE_SCATTER = 3,    /* K4 records into cell order */
+  ZB_STAGE_PAIR_COUNT = 4, /* K5 filtered pair count */
+  ZB_STAGE_PAIR_EMIT = 5,  /* K5 pair list */
+  ZB_STAGE_PAIR_LJ = 6,    /* K6 fused Lennard-Jones energy */
+  ZB_STAGE_OTHER = 7,
+  ZB_NSTAGES = 8
+};
+int zb_grid_profile(zb_grid* g, int enable);
+int zb_grid_profile_read(zb_grid* g, double* stage_ms, uint64_t* stage_launches);
+
 /* Number of kernel launches this handle has issued since creation (bench.py's gpu_launches). */
 uint64_t zb_grid_launch_count(const zb_grid* g);
 int zb_abi_version(void);

@@ -1,0 +1,104 @@
+"""CPU-side checks of the drop-in boundary: libzelll_b200.so builds, loads and exports exactly
+the symbols include/zelll_b200.h declares; without a GPU the product path fails loudly (no CPU
+fallback); host-side GridInfo helpers reproduce the reference's known answers."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "zelll_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zb_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from zelll_b200 import build as zb_build
+
+    zb_build.build()
+    from zelll_b200 import _ffi
+
+    return _ffi.load()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from zelll_b200 import _ffi
+
+    names = _declared()
+    assert len(names) >= 20
+    for nm in names:
+        assert hasattr(lib, nm), f"{nm} declared in include/zelll_b200.h but not exported"
+    assert sorted(_ffi.SIGNATURES) == names, "ctypes binding and header disagree"
+    assert lib.zb_abi_version() == _ffi.ABI_VERSION
+
+
+def test_zb_info_layout_matches_header():
+    from zelll_b200 import _ffi
+
+    # 7 doubles, 6 int32, 2 uint64, 4 int32
+    assert C.sizeof(_ffi.ZbInfo) == 7 * 8 + 6 * 4 + 2 * 8 + 4 * 4
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert lib.zb_grid_create(1, 3, 0, C.byref(h)) == 2  # ZB_ERR_CUDA
+    assert not h.value
+    import zelll_b200
+
+    with pytest.raises(zelll_b200.ZelllB200Error):
+        zelll_b200.CellGrid(np.zeros((4, 3)), 1.0)
+
+
+def test_bad_arguments_do_not_crash(lib):
+    h = C.c_void_p()
+    assert lib.zb_grid_create(7, 3, 0, C.byref(h)) == 1   # bad dtype
+    assert lib.zb_grid_create(1, 4, 0, C.byref(h)) == 1   # bad ndim
+    assert lib.zb_grid_create(1, 3, 0, None) == 1
+    lib.zb_grid_destroy(None)
+    assert lib.zb_last_error(None) == b"null handle"
+    assert lib.zb_grid_launch_count(None) == 0
+
+
+def test_gridinfo_host_helpers_match_reference_golden(golden):
+    """GridInfo::{flatten_index, try_cell_index, flat_cell_index} (util.rs:171-297) on the host."""
+    from zelll_b200 import _ffi
+    from zelll_b200.cellgrid import GridInfo
+
+    g = golden["test_utils"]
+    raw = _ffi.ZbInfo()
+    for d in range(3):
+        raw.inf[d], raw.sup[d] = g["aabb_inf"][d], g["aabb_sup"][d]
+        raw.shape[d], raw.strides[d] = g["grid_shape"][d], g["grid_strides"][d]
+    raw.cutoff, raw.ndim, raw.dtype, raw.keys_changed = g["cutoff"], 3, _ffi.F64, -1
+    info = GridInfo(raw)
+    for case in g["cell_index_cases"]:
+        assert info.try_cell_index(case["p"]) == case["cell"]
+        assert info.flat_cell_index(case["p"]) == case["flat"]
+        assert info.flatten_index(case["cell"]) == case["flat"]
+    d = golden["doctest_flat_cell_index"]
+    assert info.keys_changed is None
+    with pytest.raises(IndexError):
+        far = [info.origin()[k] - 2.5 * info.cutoff() for k in range(3)]
+        info.cell_index(far)
+    assert info.try_cell_index([info.origin()[k] - 0.5 * info.cutoff() for k in range(3)]) == [-1, -1, -1]
+
+
+def test_slab_bounds_partition():
+    from zelll_b200.sharded import grid_shape, slab_bounds
+
+    for nz in (1, 2, 7, 111112):
+        for world in (1, 2, 3, 8):
+            b = [slab_bounds(nz, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == nz
+            assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+    assert grid_shape([0.2, 0.25, 0.3], [2.7, 2.75, 2.8], 1.0, np.float64) == [3, 3, 3]

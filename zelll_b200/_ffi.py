@@ -18,6 +18,7 @@ OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_TOO_MANY, ERR_GRID_TOO_LARGE, ERR_N
 STATUS_NAMES = ["ZB_OK", "ZB_ERR_BAD_ARG", "ZB_ERR_CUDA", "ZB_ERR_CAPACITY", "ZB_ERR_TOO_MANY",
                 "ZB_ERR_GRID_TOO_LARGE", "ZB_ERR_NOT_BUILT", "ZB_ERR_OUT_OF_WINDOW"]
 ABI_VERSION = 1
+STAGES = ["bbox", "count", "scan", "scatter", "pair_count", "pair_emit", "pair_lj", "other"]
 
 
 class ZbInfo(C.Structure):
@@ -59,6 +60,8 @@ SIGNATURES = {
     "zb_grid_pairs": (_int, [_vp, _int, _dbl, _vp, _u64, _u64p]),
     "zb_grid_lj_energy": (_int, [_vp, _int, _dbl, _vp, _vp]),
     "zb_grid_query_neighbors": (_int, [_vp, _vp, _u64, _int, _dbl, _vp, _vp, _vp, _u64, _u64p]),
+    "zb_grid_profile": (_int, [_vp, _int]),
+    "zb_grid_profile_read": (_int, [_vp, _dp, _u64p]),
     "zb_grid_launch_count": (_u64, [_vp]),
 }
 

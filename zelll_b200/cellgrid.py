@@ -201,6 +201,9 @@ class CellGrid:
             t = t.reshape(-1, self.ndim).contiguous()
             if t.is_cuda and t.device.index != self.device:
                 raise ValueError(f"tensor lives on {t.device}, grid on cuda:{self.device}")
+            if t.is_cuda:
+                # device tensors are produced on torch's current stream: enqueue behind them
+                self.use_stream(torch.cuda.current_stream(t.device).cuda_stream)
             return t.data_ptr(), t.shape[0], t, None
         if isinstance(particles, np.ndarray) and particles.dtype.kind in "fiu":
             a = np.ascontiguousarray(particles, dtype=self.dtype).reshape(-1, self.ndim)
@@ -400,6 +403,23 @@ class CellGrid:
         self.__init__(state["points"], state["cutoff"], dtype=np.dtype(state["dtype"]), ndim=state["ndim"],
                       device=state["device"])
         self._label_map = state.get("label_map")
+
+    # -- streams and device timing -------------------------------------------------------------
+    def use_stream(self, cuda_stream: int) -> None:
+        """Enqueue all later work of this grid on `cuda_stream` (a cudaStream_t as int)."""
+        if getattr(self, "_stream", None) != cuda_stream:
+            self._check(self._lib.zb_grid_set_stream(self._h, C.c_void_p(cuda_stream)))
+            self._stream = cuda_stream
+
+    def profile(self, enable: bool = True) -> None:
+        self._check(self._lib.zb_grid_profile(self._h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{stage: (summed device ms, launches)} since profile(True)."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_uint64 * 8)()
+        self._check(self._lib.zb_grid_profile_read(self._h, ms, cnt))
+        return {name: (ms[k], int(cnt[k])) for k, name in enumerate(_ffi.STAGES)}
 
     @property
     def launch_count(self) -> int:

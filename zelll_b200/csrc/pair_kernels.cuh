@@ -106,6 +106,7 @@ struct CountConsumer {
     unsigned long long* block_totals; // [gridDim.x]
   };
   static constexpr int kWarpSmemBytes = 0;
+  static constexpr int kStage = 4;  // ZB_STAGE_PAIR_COUNT
   Args a;
   ConsumerSmem* cs;
   unsigned long long cnt;    // per-lane, current tile
@@ -142,6 +143,7 @@ struct EmitConsumer {
     uint2* out;
   };
   static constexpr int kWarpSmemBytes = 64 * sizeof(uint2);
+  static constexpr int kStage = 5;  // ZB_STAGE_PAIR_EMIT
   Args a;
   ConsumerSmem* cs;
   uint2* q;
@@ -191,6 +193,7 @@ struct LjConsumer {
     unsigned long long* block_totals;   // [gridDim.x]
   };
   static constexpr int kWarpSmemBytes = 64 * sizeof(T);
+  static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
   Args a;
   T* q;
   int qn;

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "build_kernels.cuh"
 #include "pair_kernels.cuh"
@@ -93,6 +94,14 @@ struct zb_grid {
   Misc* misc = nullptr;       // device
   Misc* h_misc = nullptr;     // pinned host mirror for small read-backs
   uint32_t pair_ntiles_cap = 0;
+
+  // optional per-stage device timing (zb_grid_profile): cudaEvent pairs around the hot launches
+  bool profile = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_free;
+  double stage_ms[ZB_NSTAGES] = {0};
+  uint64_t stage_launches[ZB_NSTAGES] = {0};
 };
 
 namespace {
@@ -106,6 +115,31 @@ int fail(zb_grid* g, int code, const char* fmt, ...) {
   if (g) g->err = buf;
   return code;
 }
+
+// records an event pair around one launch when profiling is on
+struct StageSpan {
+  zb_grid* g;
+  cudaEvent_t b = nullptr;
+  StageSpan(zb_grid* g_, int stage) : g(g_) {
+    if (!g->profile) return;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (auto& e : ev) {
+      if (!g->ev_free.empty()) {
+        e = g->ev_free.back();
+        g->ev_free.pop_back();
+      } else if (cudaEventCreate(&e) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+      }
+    }
+    cudaEventRecord(ev[0], g->stream);
+    b = ev[1];
+    g->spans.push_back({stage, ev[0], ev[1]});
+  }
+  ~StageSpan() {
+    if (b) cudaEventRecord(b, g->stream);
+  }
+};
 
 #define ZB_CUDA(expr)                                                                          \
   do {                                                                                         \
@@ -194,6 +228,7 @@ int launch_bbox(zb_grid* g, const T* xyz, uint64_t n) {
   T* partials = static_cast<T*>(g->partials.p);
   T* out6 = reinterpret_cast<T*>(g->misc->out6);
   unsigned* ticket = &g->misc->ticket;
+  StageSpan span(g, ZB_STAGE_BBOX);
   if (g->ndim == 3) {
     if (aligned) bbox_kernel<T, 3, V><<<blocks, kBboxThreads, 0, g->stream>>>(xyz, n, partials, ticket, out6);
     else bbox_kernel<T, 3, 1><<<blocks, kBboxThreads, 0, g->stream>>>(xyz, n, partials, ticket, out6);
@@ -272,6 +307,7 @@ int build_sorted(zb_grid* g, const T* xyz, const uint32_t* labels, uint64_t n) {
   const GridParams<T> p = make_params<T>(g);
   uint32_t* cursor = cursor_ptr(g);
   if (n > 0) {
+    StageSpan span(g, ZB_STAGE_COUNT);
     const uint32_t blocks = (uint32_t)((n + kPointThreads - 1) / kPointThreads);
     if (g->ndim == 3)
       count_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
@@ -279,11 +315,15 @@ int build_sorted(zb_grid* g, const T* xyz, const uint32_t* labels, uint64_t n) {
       count_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
     g->launches++;
   }
-  scan_kernel<<<ntile, kScanThreads, 0, g->stream>>>(cursor, (uint32_t)nc,
-                                                     static_cast<unsigned long long*>(g->scan_state.p),
-                                                     &g->misc->tile_counter, &g->misc->nonempty);
+  {
+    StageSpan span(g, ZB_STAGE_SCAN);
+    scan_kernel<<<ntile, kScanThreads, 0, g->stream>>>(cursor, (uint32_t)nc,
+                                                       static_cast<unsigned long long*>(g->scan_state.p),
+                                                       &g->misc->tile_counter, &g->misc->nonempty);
+  }
   g->launches++;
   if (n > 0) {
+    StageSpan span(g, ZB_STAGE_SCATTER);
     const uint32_t blocks = (uint32_t)((n + kPointThreads - 1) / kPointThreads);
     Rec<T>* sorted = static_cast<Rec<T>*>(g->sorted.p);
     if (g->ndim == 3)
@@ -488,7 +528,10 @@ template <class T, class Consumer>
 int launch_pairs(zb_grid* g, int cmp, const PairPlan& pl, const PairParams<T>& p, typename Consumer::Args args) {
   auto go = [&](auto kern) -> int {
     ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    kern<<<pl.blocks, kPairThreads, pl.smem, g->stream>>>(p, args);
+    {
+      StageSpan span(g, Consumer::kStage);
+      kern<<<pl.blocks, kPairThreads, pl.smem, g->stream>>>(p, args);
+    }
     g->launches++;
     ZB_CUDA(cudaGetLastError());
     return ZB_OK;
@@ -623,6 +666,11 @@ void zb_grid_destroy(zb_grid* g) {
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
                     &g->block_energy, &g->block_totals, &g->out_stage};
   for (DevBuf* b : bufs) free_buf(*b);
+  for (auto& sp : g->spans) {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  for (auto e : g->ev_free) cudaEventDestroy(e);
   if (g->misc) cudaFree(g->misc);
   if (g->h_misc) cudaFreeHost(g->h_misc);
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
@@ -986,6 +1034,44 @@ int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cm
   if (g->dtype == ZB_F32) ZB_TRY(run(float(), true, dl));
   else ZB_TRY(run(double(), true, dl));
   if (!ldev) ZB_TRY(deliver(g, labels, dl, total * 4));
+  return ZB_OK;
+}
+
+int zb_grid_profile(zb_grid* g, int enable) {
+  ZB_TRY(enter(g));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  for (auto& sp : g->spans) {
+    g->ev_free.push_back(sp.a);
+    g->ev_free.push_back(sp.b);
+  }
+  g->spans.clear();
+  for (int i = 0; i < ZB_NSTAGES; ++i) {
+    g->stage_ms[i] = 0.0;
+    g->stage_launches[i] = 0;
+  }
+  g->profile = enable != 0;
+  return ZB_OK;
+}
+
+int zb_grid_profile_read(zb_grid* g, double* stage_ms, uint64_t* stage_launches) {
+  ZB_TRY(enter(g));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  for (auto& sp : g->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.stage >= 0 && sp.stage < ZB_NSTAGES) {
+      g->stage_ms[sp.stage] += (double)ms;
+      g->stage_launches[sp.stage] += 1;
+    } else {
+      cudaGetLastError();
+    }
+    g->ev_free.push_back(sp.a);
+    g->ev_free.push_back(sp.b);
+  }
+  g->spans.clear();
+  for (int i = 0; i < ZB_NSTAGES; ++i) {
+    if (stage_ms) stage_ms[i] = g->stage_ms[i];
+    if (stage_launches) stage_launches[i] = g->stage_launches[i];
+  }
   return ZB_OK;
 }
 
