@@ -1,4 +1,4 @@
-"""Ad-hoc timing of rebuild / pair_count / lj_energy with device-resident input (CUDA events)."""
+"""Ad-hoc timing of rebuild / pair_count / lj_energy with device-resident input (stage profile)."""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -11,16 +11,20 @@ def main():
     pts = workload.generate_points_random(n, dtype=dtype)
     t = torch.from_numpy(pts).cuda()
     cg = zelll_b200.CellGrid(t, 10.0, dtype=dtype)
+    res = {}
     for name, fn in [("rebuild", lambda: cg.rebuild(t)), ("pair_count_le", lambda: cg.pair_count(10.0, "le")),
+                     ("pair_count_none", lambda: cg.pair_count()),
                      ("lj_energy", lambda: cg.lj_energy(10.0, "lt")),
                      ("rebuild+lj", lambda: (cg.rebuild(t), cg.lj_energy(10.0, "lt")))]:
         for _ in range(3): fn()
         torch.cuda.synchronize()
+        cg.profile(True)
         t0 = time.perf_counter()
         reps = 10
         for _ in range(reps): r = fn()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
-        print(f"{name:16s} n={n:.0e} {dtype.__name__}: {dt*1e3:8.3f} ms   result={r}")
-    print("info", cg.info().shape(), cg.info().n_cells)
+        st = {k: round(v[0] / v[1], 4) for k, v in cg.profile_read().items() if v[1]}
+        cg.profile(False)
+        print(f"{name:16s} n={n:.0e} {dtype.__name__}: {dt*1e3:8.3f} ms  stages(ms)={st} result={r}")
 main()

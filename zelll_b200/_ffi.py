@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzelll_b200.so")
+LIB_PATH = os.environ.get("ZB_LIB") or os.path.join(HERE, "libzelll_b200.so")  # ZB_LIB: experiment builds
 
 F32, F64 = 0, 1
 CMP_NONE, CMP_LT, CMP_LE = 0, 1, 2

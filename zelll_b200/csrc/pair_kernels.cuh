@@ -27,15 +27,45 @@
 //
 // Arithmetic.  dsq = (dx*dx + dy*dy) + dz*dz with separately rounded operations, exactly what
 // nalgebra::distance_squared does (benches/lj.rs:84); the TU is compiled with -fmad=false.
+//
+// f32 prefilter for f64 grids.  FP64 issue, not HBM, bounds the f64 distance test on B200 (9 DP
+// instructions per test at 4 cycles per warp instruction and SM sub-partition).  Staged tiles
+// therefore also keep every record as float4 coordinates RELATIVE to the tile's first record;
+// the test loop runs in f32 (FFMA allowed) and classifies each pair against a guard band around
+// the threshold that is wider than the worst-case f32 error (derivation at prefilter_band()).
+// Sure misses -- 80 % of the tests -- never touch the FP64 pipe; everything else is re-evaluated
+// from the f64 records with the reference's exact arithmetic, so the pair set stays bit-exact.
 #pragma once
 
 #include "common.cuh"
 
 namespace zb {
 
-constexpr int kPairThreads = 256;
+#ifndef ZB_PAIR_THREADS
+#define ZB_PAIR_THREADS 256
+#endif
+#ifndef ZB_PAIR_MINBLOCKS
+#define ZB_PAIR_MINBLOCKS 4
+#endif
+#ifndef ZB_PAIR_UNROLL
+#define ZB_PAIR_UNROLL 4
+#endif
+constexpr int kPairThreads = ZB_PAIR_THREADS;
+constexpr int kPairUnroll = ZB_PAIR_UNROLL;
+constexpr int kMaxNJ = 4;  // candidates held in registers per lane (register tile of the cell loop)
+constexpr int kQueueSlots = 32 + 32 * kMaxNJ;  // per-warp hit queue: one full row + one iteration's worth
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kStageCells = 512;  // staged CSR entries per tile (cells + halo + 1)
+
+// unsigned division by a launch-time constant (cell id -> cell coordinates) without the ~20
+// instruction integer-division sequence: q = (t + ((n - t) >> sh1)) >> sh2, t = umulhi(n, mul)
+struct FastDiv {
+  uint32_t mul, sh1, sh2;
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
 
 template <class T>
 struct PairParams {
@@ -47,6 +77,10 @@ struct PairParams {
   uint32_t ntiles;
   uint32_t stage_recs;  // capacity of the record stage buffer
   T c2;                 // squared filter radius, in T (cutoff.powi(2))
+  T fc;                 // filter radius
+  T cell;               // edge length of a grid cell (the grid's cutoff)
+  int prefilter;        // f64 only: run staged tiles through the f32 prefilter
+  FastDiv div0, div1;   // division by w0 and by w1
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -91,11 +125,94 @@ __device__ __forceinline__ T lj_term(T dsq) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Consumers.  hit() is called by all 32 lanes of a warp in convergence, once per distance test.
+// small helpers
+
+template <int N>
+struct IntTag {
+  static constexpr int value = N;
+};
+
+// candidates per lane of the exact loop.  Measured on B200 (n = 10^7 benchmark box): holding 4
+// candidates per lane raises register use to ~128 and makes the LJ consumer 2-3x slower, while
+// the count consumer does not move (the loop is instruction-issue bound either way): keep 1.
+template <class T>
+struct GenericNJ {
+  static constexpr int value = 1;
+};
+
+// opaque copy: keeps a kernel parameter in registers instead of re-reading the constant bank
+__device__ __forceinline__ float keep_in_reg(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+__device__ __forceinline__ double keep_in_reg(double v) {
+  asm volatile("" : "+d"(v));
+  return v;
+}
+
+// coordinates (and, when the consumer wants it, the label) of one record
+template <bool LABEL>
+__device__ __forceinline__ void load_part(const Rec<float>* p, float& x, float& y, float& z, uint32_t& label) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  x = v.x; y = v.y; z = v.z;
+  label = LABEL ? __float_as_uint(v.w) : 0u;
+}
+template <bool LABEL>
+__device__ __forceinline__ void load_part(const Rec<double>* p, double& x, double& y, double& z, uint32_t& label) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  x = a.x; y = a.y;
+  if (LABEL) {
+    const double2 b = reinterpret_cast<const double2*>(p)[1];
+    z = b.x;
+    label = (uint32_t)(__double_as_longlong(b.y) & 0xffffffffll);
+  } else {
+    z = reinterpret_cast<const double*>(p)[2];
+    label = 0u;
+  }
+}
+
+// the reference's distance_squared between two records, optionally with their labels
+template <class T, bool LABEL>
+__device__ __forceinline__ T exact_dsq(const Rec<T>* a, const Rec<T>* b, uint32_t& la, uint32_t& lb) {
+  T xa, ya, za, xb, yb, zb_;
+  load_part<LABEL>(a, xa, ya, za, la);
+  load_part<LABEL>(b, xb, yb, zb_, lb);
+  const T dx = xa - xb, dy = ya - yb, dz = za - zb_;
+  return (dx * dx + dy * dy) + dz * dz;
+}
+
+template <int CMP, class T>
+__device__ __forceinline__ bool passes(T dsq, T c2) {
+  return CMP == 0 ? true : (CMP == 1 ? dsq < c2 : dsq <= c2);
+}
+
+// Guard band of the f32 prefilter.  Let o be the tile origin, R >= |x_p - o| for every staged
+// record and axis, u = 2^-24.  The staged f32 coordinate r_p = fl32(x_p - o) is off by <= u R;
+// d32 = fl32(r_i - r_j) is off the true difference d by <= 2 u R + u |d|; the three squares and two
+// sums (FMA or not) add <= 3 u dsq.  Near the threshold |d| <= fc per axis and
+// |dx| + |dy| + |dz| <= sqrt(3) fc, so |dsq32 - dsq| <= u (7 fc R + 6.5 fc^2): relative to fc^2 that
+// is u (7 R / fc + 6.5).  We use delta = 2 u (8 R / fc + 8), more than twice the bound (this also
+// covers the f64 roundings of the reference's own dsq and of x_p - o, ~2^-52, and the directed
+// rounding of the two f32 thresholds).  dsq32 < c2 (1 - delta) => certainly inside; dsq32 >
+// c2 (1 + delta) => certainly outside; in between the pair is decided in f64.
+__device__ __forceinline__ float prefilter_delta(float R_over_fc) {
+  return 1.1920929e-7f * (8.0f * R_over_fc + 8.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Consumers.  test_n() (exact loop) / maybe_n() (prefilter loop) are called by all 32 lanes of a
+// warp in convergence, once per home particle with the NJ candidates a lane holds.
 
 struct ConsumerSmem {
   unsigned long long tile_count;  // CountConsumer
   uint32_t cursor;                // EmitConsumer
+};
+
+// what the prefilter path needs to re-evaluate a pair exactly: staged records by tile-local position
+template <class T>
+struct ExactCtx {
+  const Rec<T>* rec;
+  T c2;
 };
 
 // -- count -----------------------------------------------------------------------------------
@@ -107,17 +224,55 @@ struct CountConsumer {
   };
   static constexpr int kWarpSmemBytes = 0;
   static constexpr int kStage = 4;  // ZB_STAGE_PAIR_COUNT
+  static constexpr bool kNeedLabels = false;
+  static constexpr bool kCountsOnly = true;
   Args a;
   ConsumerSmem* cs;
+  ExactCtx<T> ex;
+  uint32_t c32;              // per-lane, current chunk (one predicated add per test)
   unsigned long long cnt;    // per-lane, current tile
   unsigned long long total;  // thread 0: this block's running total
 
-  __device__ CountConsumer(const Args& args, ConsumerSmem* s, void*) : a(args), cs(s), cnt(0), total(0) {}
-  __device__ __forceinline__ void tile_begin(uint32_t) {
+  __device__ CountConsumer(const Args& args, ConsumerSmem* s, void*, T c2) : a(args), cs(s), c32(0), cnt(0), total(0) {
+    ex.rec = nullptr;
+    ex.c2 = c2;
+  }
+  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>* staged, bool) {
     if (threadIdx.x == 0) cs->tile_count = 0;
     cnt = 0;
+    ex.rec = staged;
   }
-  __device__ __forceinline__ void hit(bool h, T, uint32_t, uint32_t) { cnt += h ? 1u : 0u; }
+  template <int NJ>
+  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], uint32_t, const uint32_t (&)[NJ]) {
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) c32 += h[q] ? 1u : 0u;
+  }
+  // prefilter: sure hits are counted at once; the rare in-band pair is decided in f64 on the spot
+  template <int CMP, int NJ>
+  __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&sure)[NJ], uint32_t ipos,
+                                          const uint32_t (&jpos)[NJ]) {
+    bool amb = false;
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+      c32 += sure[q] ? 1u : 0u;
+      amb = amb || (maybe[q] && !sure[q]);
+    }
+    if (__any_sync(0xffffffffu, amb)) {
+#pragma unroll
+      for (int q = 0; q < NJ; ++q)
+        if (maybe[q] && !sure[q]) {
+          uint32_t la, lb;
+          const T d = exact_dsq<T, false>(ex.rec + ipos, ex.rec + jpos[q], la, lb);
+          c32 += passes<CMP>(d, ex.c2) ? 1u : 0u;
+        }
+    }
+  }
+  __device__ __forceinline__ void add(uint32_t k) { cnt += k; }  // unfiltered candidates, no loop
+  __device__ __forceinline__ void chunk_end() {
+    cnt += c32;
+    c32 = 0;
+  }
+  template <int CMP>
   __device__ __forceinline__ void tile_end(uint32_t tile) {
     unsigned long long w = warp_reduce(cnt, [](unsigned long long x, unsigned long long y) { return x + y; });
     if (lane_id() == 0 && w) atomicAdd(&cs->tile_count, w);
@@ -135,47 +290,101 @@ struct CountConsumer {
 // -- emit ------------------------------------------------------------------------------------
 // Each tile owns the output range [tile_offsets[tile], tile_offsets[tile+1]) computed from a
 // previous CountConsumer pass, so the list is compact and needs no global atomics: warps stage
-// hits in a 64-entry shared queue and claim 32 slots at a time from the tile's shared cursor.
+// hits in a shared queue and claim slots 32 at a time from the tile's shared cursor.
 template <class T>
 struct EmitConsumer {
   struct Args {
     const unsigned long long* tile_offsets;  // [ntiles + 1]
     uint2* out;
   };
-  static constexpr int kWarpSmemBytes = 64 * sizeof(uint2);
+  static constexpr int kWarpSmemBytes = kQueueSlots * sizeof(uint2);
   static constexpr int kStage = 5;  // ZB_STAGE_PAIR_EMIT
+  static constexpr bool kNeedLabels = true;
+  static constexpr bool kCountsOnly = false;
   Args a;
   ConsumerSmem* cs;
-  uint2* q;
-  int qn;
+  ExactCtx<T> ex;
+  uint2* q;        // exact loop: (label, label) rows; prefilter loop: packed (ipos << 16 | jpos) in .x
+  uint32_t qn;
+  bool pf;
+  unsigned ltmask;
   unsigned long long base;
 
-  __device__ EmitConsumer(const Args& args, ConsumerSmem* s, void* warp_smem)
-      : a(args), cs(s), q(static_cast<uint2*>(warp_smem)), qn(0), base(0) {}
-  __device__ __forceinline__ void tile_begin(uint32_t tile) {
+  __device__ EmitConsumer(const Args& args, ConsumerSmem* s, void* warp_smem, T c2)
+      : a(args), cs(s), q(static_cast<uint2*>(warp_smem)), qn(0), pf(false), ltmask(lanemask_lt()), base(0) {
+    ex.rec = nullptr;
+    ex.c2 = c2;
+  }
+  __device__ __forceinline__ void tile_begin(uint32_t tile, const Rec<T>* staged, bool prefilter) {
     if (threadIdx.x == 0) cs->cursor = 0;
     base = a.tile_offsets[tile];
     qn = 0;
+    ex.rec = staged;
+    pf = prefilter;
   }
-  __device__ __forceinline__ void flush(int count) {
-    __syncwarp();
-    qn -= count;
+  // write the rows for which `h` holds to the tile's output range
+  __device__ __forceinline__ void put(bool h, uint2 row) {
+    const unsigned b = __ballot_sync(0xffffffffu, h);
+    if (b == 0) return;
     uint32_t pos = 0;
-    if (lane_id() == 0) pos = atomicAdd(&cs->cursor, (uint32_t)count);
+    if (lane_id() == 0) pos = atomicAdd(&cs->cursor, (uint32_t)__popc(b));
     pos = __shfl_sync(0xffffffffu, pos, 0);
-    if ((int)lane_id() < count) a.out[base + pos + lane_id()] = q[qn + lane_id()];
-    __syncwarp();
+    if (h) a.out[base + pos + __popc(b & ltmask)] = row;
   }
-  __device__ __forceinline__ void hit(bool h, T, uint32_t li, uint32_t lj) {
-    unsigned b = __ballot_sync(0xffffffffu, h);
-    if (b) {
-      if (h) q[qn + __popc(b & lanemask_lt())] = make_uint2(li, lj);
-      qn += __popc(b);
-      if (qn >= 32) flush(32);
+  __device__ __forceinline__ void drain_exact_rows() {
+    while (qn >= 32) {
+      __syncwarp();
+      qn -= 32;
+      put(true, q[qn + lane_id()]);
+      __syncwarp();
     }
   }
+  template <int CMP>
+  __device__ __forceinline__ void drain_pf_row(bool valid, uint32_t entry) {
+    uint32_t la = 0, lb = 0;
+    bool h = false;
+    if (valid) {
+      const T d = exact_dsq<T, true>(ex.rec + (entry >> 16), ex.rec + (entry & 0xffffu), la, lb);
+      h = passes<CMP>(d, ex.c2);
+    }
+    put(h, make_uint2(la, lb));
+  }
+  template <int NJ>
+  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], uint32_t li, const uint32_t (&lj)[NJ]) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, h[k]);
+      if (h[k]) q[qn + __popc(b & ltmask)] = make_uint2(li, lj[k]);
+      qn += __popc(b);
+    }
+    drain_exact_rows();
+  }
+  template <int CMP, int NJ>
+  __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&)[NJ], uint32_t ipos,
+                                          const uint32_t (&jpos)[NJ]) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, maybe[k]);
+      if (maybe[k]) q[qn + __popc(b & ltmask)].x = (ipos << 16) | jpos[k];
+      qn += __popc(b);
+    }
+    while (qn >= 32) {
+      __syncwarp();
+      qn -= 32;
+      drain_pf_row<CMP>(true, q[qn + lane_id()].x);
+      __syncwarp();
+    }
+  }
+  __device__ __forceinline__ void add(uint32_t) {}
+  __device__ __forceinline__ void chunk_end() {}
+  template <int CMP>
   __device__ __forceinline__ void tile_end(uint32_t) {
-    if (qn > 0) flush(qn);
+    __syncwarp();
+    if (qn > 0) {
+      if (pf) drain_pf_row<CMP>(lane_id() < qn, lane_id() < qn ? q[lane_id()].x : 0u);
+      else put(lane_id() < qn, q[lane_id() < qn ? lane_id() : 0]);
+      qn = 0;
+    }
     __syncthreads();
   }
   __device__ __forceinline__ void finish() {}
@@ -183,143 +392,335 @@ struct EmitConsumer {
 
 // -- Lennard-Jones energy ----------------------------------------------------------------------
 // Hits are ~20 % of the tests, so evaluating lj() under the hit predicate would run the
-// division at ~6/32 lane efficiency.  Instead hits' dsq are compacted into a per-warp shared
-// queue and evaluated 32 at a time.  Per-lane f64 partial sums -> warp shuffle -> block ->
-// block_energy[blockIdx]; a last single-block kernel folds those in fixed order.
+// division at ~6/32 lane efficiency.  Instead hits are compacted (ballot + popc) into a per-warp
+// shared queue and evaluated 32 at a time with all lanes busy: the exact loop queues dsq, the
+// prefilter loop queues the pair's tile-local positions and the drain recomputes dsq in f64.
+// Per-lane f64 partial sums -> warp shuffle -> block -> block_energy[blockIdx]; finalize_kernel
+// folds those in fixed order.
 template <class T>
 struct LjConsumer {
   struct Args {
     double* block_energy;               // [gridDim.x]
     unsigned long long* block_totals;   // [gridDim.x]
   };
-  static constexpr int kWarpSmemBytes = 64 * sizeof(T);
+  // exact loop: (32 + 32 NJ) dsq values; prefilter loop (f64 only): kQueueSlots packed positions
+  static constexpr int kExactBytes = (32 + 32 * GenericNJ<T>::value) * (int)sizeof(T);
+  static constexpr int kPfBytes = sizeof(T) == 8 ? kQueueSlots * 4 : 0;
+  static constexpr int kWarpSmemBytes = kExactBytes > kPfBytes ? kExactBytes : kPfBytes;
   static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
+  static constexpr bool kNeedLabels = false;
+  static constexpr bool kCountsOnly = false;
   Args a;
-  T* q;
-  int qn;
+  ExactCtx<T> ex;
+  T* q;          // exact loop: dsq; prefilter loop: uint32 (ipos << 16 | jpos) in the same bytes
+  uint32_t qn;   // warp-uniform fill level
+  bool pf;
+  unsigned ltmask;
   double acc;
-  unsigned long long cnt;  // warp-uniform
+  unsigned long long cnt;  // per-lane pairs kept
 
-  __device__ LjConsumer(const Args& args, ConsumerSmem*, void* warp_smem)
-      : a(args), q(static_cast<T*>(warp_smem)), qn(0), acc(0.0), cnt(0) {}
-  __device__ __forceinline__ void tile_begin(uint32_t) {}
-  __device__ __forceinline__ void hit(bool h, T dsq, uint32_t, uint32_t) {
-    unsigned b = __ballot_sync(0xffffffffu, h);
-    if (b) {
-      if (h) q[qn + __popc(b & lanemask_lt())] = dsq;
-      int k = __popc(b);
-      qn += k;
-      cnt += (unsigned)k;
-      if (qn >= 32) {
-        __syncwarp();
-        qn -= 32;
-        T d = q[qn + lane_id()];
-        acc += (double)lj_term(d);
-        __syncwarp();
-      }
+  __device__ LjConsumer(const Args& args, ConsumerSmem*, void* warp_smem, T c2)
+      : a(args), q(static_cast<T*>(warp_smem)), qn(0), pf(false), ltmask(lanemask_lt()), acc(0.0), cnt(0) {
+    ex.rec = nullptr;
+    ex.c2 = c2;
+  }
+  __device__ __forceinline__ uint32_t* q32() { return reinterpret_cast<uint32_t*>(q); }
+  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>* staged, bool prefilter) {
+    ex.rec = staged;
+    pf = prefilter;
+  }
+  template <int CMP>
+  __device__ __forceinline__ void drain_pf_row(bool valid, uint32_t entry) {
+    uint32_t la, lb;
+    // idle lanes evaluate pair (0, 0) harmlessly: dsq = 0 never reaches the sum
+    const T d = exact_dsq<T, false>(ex.rec + (entry >> 16), ex.rec + (entry & 0xffffu), la, lb);
+    const bool h = valid && passes<CMP>(d, ex.c2);
+    const T e = lj_term(d);
+    if (h) {
+      acc += (double)e;
+      cnt += 1;
     }
   }
-  __device__ __forceinline__ void tile_end(uint32_t) { __syncthreads(); }
-  __device__ __forceinline__ void finish() {
+  template <int NJ>
+  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&dsq)[NJ], uint32_t, const uint32_t (&)[NJ]) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, h[k]);
+      if (h[k]) q[qn + __popc(b & ltmask)] = dsq[k];
+      qn += __popc(b);
+    }
+    while (qn >= 32) {
+      __syncwarp();
+      qn -= 32;
+      acc += (double)lj_term(q[qn + lane_id()]);
+      cnt += 1;
+      __syncwarp();
+    }
+  }
+  template <int CMP, int NJ>
+  __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&)[NJ], uint32_t ipos,
+                                          const uint32_t (&jpos)[NJ]) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, maybe[k]);
+      if (maybe[k]) q32()[qn + __popc(b & ltmask)] = (ipos << 16) | jpos[k];
+      qn += __popc(b);
+    }
+    while (qn >= 32) {
+      __syncwarp();
+      qn -= 32;
+      drain_pf_row<CMP>(true, q32()[qn + lane_id()]);
+      __syncwarp();
+    }
+  }
+  __device__ __forceinline__ void add(uint32_t) {}
+  __device__ __forceinline__ void chunk_end() {}
+  template <int CMP>
+  __device__ __forceinline__ void tile_end(uint32_t) {
+    // the queue refers to this tile's stage: empty it before the stage is reused
     __syncwarp();
-    if ((int)lane_id() < qn) acc += (double)lj_term(q[lane_id()]);
+    if (qn > 0) {
+      const bool v = lane_id() < qn;
+      if (pf) {
+        drain_pf_row<CMP>(v, v ? q32()[lane_id()] : 0u);
+      } else if (v) {
+        acc += (double)lj_term(q[lane_id()]);
+        cnt += 1;
+      }
+      qn = 0;
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void finish() {
     __shared__ double s_e[kPairWarps];
     __shared__ unsigned long long s_c[kPairWarps];
-    double w = warp_reduce(acc, [](double x, double y) { return x + y; });
+    const double w = warp_reduce(acc, [](double x, double y) { return x + y; });
+    const unsigned long long c = warp_reduce(cnt, [](unsigned long long x, unsigned long long y) { return x + y; });
     if (lane_id() == 0) {
       s_e[threadIdx.x >> 5] = w;
-      s_c[threadIdx.x >> 5] = cnt;
+      s_c[threadIdx.x >> 5] = c;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       double e = 0.0;
-      unsigned long long c = 0;
-      for (int i = 0; i < kPairWarps; ++i) { e += s_e[i]; c += s_c[i]; }
+      unsigned long long t = 0;
+      for (int i = 0; i < kPairWarps; ++i) { e += s_e[i]; t += s_c[i]; }
       a.block_energy[blockIdx.x] = e;
-      a.block_totals[blockIdx.x] = c;
+      a.block_totals[blockIdx.x] = t;
     }
   }
 };
 
 // ---------------------------------------------------------------------------------------------
-// One warp enumerates the half-shell pairs of home cell c.
-//   STAGED: records and CSR entries come from shared memory (rec[-rec_origin], csr[-csr_origin]).
-template <class T, int CMP, bool STAGED, class Consumer>
-__device__ __forceinline__ void process_cell(const PairParams<T>& p, uint32_t c, const Rec<T>* __restrict__ rec,
-                                             uint32_t rec_origin, const uint32_t* __restrict__ csr,
-                                             uint32_t csr_origin, Consumer& cons) {
-  auto CS = [&](uint32_t cell) -> uint32_t {
-    return STAGED ? csr[cell - csr_origin] : __ldg(csr + cell);
-  };
-  const uint32_t hb = CS(c), he = CS(c + 1);
-  const uint32_t m = he - hb;
-  if (m == 0) return;
+// The candidate set of home cell c: 5 runs of consecutive records (see the header comment).
+struct CellRuns {
+  uint32_t hb, m;                 // home cell: first record, size
+  uint32_t o1, o2, o3, o4, K;     // run boundaries in candidate numbering; K = number of candidates
+  uint32_t shA, shB, shC, shD, shE;  // candidate k of run X is record k + shX
+  uint32_t first_home;            // candidates [first_home, K) are the home cell itself
 
+  // record of candidate k, or hb for an idle lane
+  __device__ __forceinline__ uint32_t pos(uint32_t k) const {
+    const uint32_t sh = k < o1 ? shA : (k < o2 ? shB : (k < o3 ? shC : (k < o4 ? shD : shE)));
+    return k < K ? k + sh : hb;
+  }
+  // number of leading home particles candidate k pairs with: all m for a candidate of another
+  // cell, the u particles before it for the home cell's u-th particle (intra-cell pairs: j
+  // after i, iters.rs:29-36), none for an idle lane
+  __device__ __forceinline__ uint32_t thr(uint32_t k) const {
+    return k < K ? (k >= first_home ? k - first_home : m) : 0u;
+  }
+};
+
+template <class T>
+__device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, const uint32_t* __restrict__ csrb,
+                                          CellRuns& r) {
+  const uint32_t hb = csrb[c], he = csrb[c + 1];
+  r.hb = hb;
+  r.m = he - hb;
+  if (r.m == 0) return false;
   const uint32_t w0 = (uint32_t)p.w0, w1 = (uint32_t)p.w1;
-  const uint32_t cx = c % w0, r = c / w0;
-  const uint32_t cy = r % w1, cz = r / w1;
+  const uint32_t row = fast_div(c, p.div0), cx = c - row * w0;
+  const uint32_t cz = fast_div(row, p.div1), cy = row - cz * w1;
   const uint32_t xl = cx > 0 ? 1u : 0u, xr = (cx + 1 < w0) ? 1u : 0u;
-  const uint32_t plane = w0 * w1;
-
-  // the 5 runs as record ranges [s, s+l)
   uint32_t sA = 0, lA = 0, sB = 0, lB = 0, sC = 0, lC = 0, sD = 0, lD = 0;
   if (cz > 0) {
-    const uint32_t cb = c - plane;
-    if (cy > 0) { sA = CS(cb - w0 - xl); lA = CS(cb - w0 + xr + 1) - sA; }
-    { sB = CS(cb - xl); lB = CS(cb + xr + 1) - sB; }
-    if (cy + 1 < w1) { sC = CS(cb + w0 - xl); lC = CS(cb + w0 + xr + 1) - sC; }
+    const uint32_t* cb = csrb + (c - w0 * w1);
+    if (cy > 0) { sA = cb[-(int)(w0 + xl)]; lA = cb[-(int)w0 + (int)xr + 1] - sA; }
+    { sB = cb[-(int)xl]; lB = cb[xr + 1] - sB; }
+    if (cy + 1 < w1) { sC = cb[w0 - xl]; lC = cb[w0 + xr + 1] - sC; }
   }
-  if (cy > 0) { sD = CS(c - w0 - xl); lD = CS(c - w0 + xr + 1) - sD; }
-  const uint32_t sE = CS(c - xl), lE = he - sE;
+  if (cy > 0) { sD = csrb[c - w0 - xl]; lD = csrb[c - w0 + xr + 1] - sD; }
+  const uint32_t sE = xl ? csrb[c - 1] : hb, lE = he - sE;
+  r.o1 = lA; r.o2 = r.o1 + lB; r.o3 = r.o2 + lC; r.o4 = r.o3 + lD; r.K = r.o4 + lE;
+  r.shA = sA; r.shB = sB - r.o1; r.shC = sC - r.o2; r.shD = sD - r.o3; r.shE = sE - r.o4;
+  r.first_home = r.K - r.m;
+  return true;
+}
 
-  const uint32_t o1 = lA, o2 = o1 + lB, o3 = o2 + lC, o4 = o3 + lD, K = o4 + lE;
-  const uint32_t shA = sA, shB = sB - o1, shC = sC - o2, shD = sD - o3, shE = sE - o4;
-  const uint32_t first_home = K - m;  // candidates [first_home, K) are the home cell itself
-  const unsigned lane = lane_id();
-  const Rec<T>* home = rec + (hb - rec_origin);
-
-  for (uint32_t kb = 0; kb < K; kb += 32) {
-    const uint32_t k = kb + lane;
-    const bool valid = k < K;
-    const uint32_t sh = k < o1 ? shA : (k < o2 ? shB : (k < o3 ? shC : (k < o4 ? shD : shE)));
-    const uint32_t pos = valid ? k + sh : hb;
-    const Rec<T> rj = load_rec(rec + (pos - rec_origin));
-    // position of candidate j inside the home cell; huge for other cells, 0 for idle lanes:
-    // the pair (i, j) is taken iff u > i  (intra-cell: j after i, iters.rs:29-36)
-    const uint32_t u = valid ? (k - first_home) : 0u;
-#pragma unroll 2
-    for (uint32_t i = 0; i < m; ++i) {
-      const Rec<T> ri = load_rec(home + i);
-      bool h = u > i;
-      T dsq = T(0);
+// ---------------------------------------------------------------------------------------------
+// Exact loop: one warp enumerates the half-shell pairs of home cell c in the arithmetic of T.
+//   recb / csrb are biased base pointers: recb[pos] is record `pos` of the cell-sorted array and
+//   csrb[cell] its CSR entry, whether they live in shared memory (staged tile) or in global memory.
+//   Every lane keeps NJ candidates j in registers; the home particles i are broadcast loads.
+template <class T, int CMP, int NJ, class Consumer>
+__device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uint32_t m, const T (&xj)[NJ],
+                                            const T (&yj)[NJ], const T (&zj)[NJ], const uint32_t (&lj)[NJ],
+                                            const uint32_t (&thr)[NJ], T c2, Consumer& cons) {
+#pragma unroll kPairUnroll
+  for (uint32_t i = 0; i < m; ++i) {
+    T xi, yi, zi;
+    uint32_t li;
+    load_part<Consumer::kNeedLabels>(home + i, xi, yi, zi, li);
+    bool h[NJ];
+    T dsq[NJ];
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+      h[q] = i < thr[q];
+      dsq[q] = T(0);
       if (CMP != 0) {
-        const T dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
-        dsq = (dx * dx + dy * dy) + dz * dz;
-        h = h && (CMP == 1 ? dsq < p.c2 : dsq <= p.c2);
+        const T dx = xi - xj[q], dy = yi - yj[q], dz = zi - zj[q];
+        dsq[q] = (dx * dx + dy * dy) + dz * dz;
+        h[q] = h[q] && passes<CMP>(dsq[q], c2);
       }
-      cons.hit(h, dsq, ri.label, rj.label);
     }
+    cons.template test_n<NJ>(h, dsq, li, lj);
+  }
+}
+
+template <class T, int CMP, class Consumer>
+__device__ __forceinline__ void process_cell(const PairParams<T>& p, uint32_t c, const Rec<T>* __restrict__ recb,
+                                             const uint32_t* __restrict__ csrb, T c2, Consumer& cons) {
+  constexpr int NJMAX = GenericNJ<T>::value;
+  CellRuns r;
+  if (!cell_runs(p, c, csrb, r)) return;
+  const unsigned lane = lane_id();
+  const Rec<T>* home = recb + r.hb;
+  for (uint32_t kb = 0; kb < r.K; kb += 32 * NJMAX) {
+    T xj[NJMAX], yj[NJMAX], zj[NJMAX];
+    uint32_t lj[NJMAX], thr[NJMAX];
+    uint32_t sum_thr = 0;
+#pragma unroll
+    for (int q = 0; q < NJMAX; ++q) {
+      const uint32_t k = kb + 32u * q + lane;
+      thr[q] = r.thr(k);
+      sum_thr += thr[q];
+      if (!(CMP == 0 && Consumer::kCountsOnly) && kb + 32u * q < r.K)
+        load_part<Consumer::kNeedLabels>(recb + r.pos(k), xj[q], yj[q], zj[q], lj[q]);
+    }
+    if (CMP == 0 && Consumer::kCountsOnly) {
+      cons.add(sum_thr);  // unfiltered count: no per-pair work
+      continue;
+    }
+    const uint32_t nj = min((r.K - kb + 31u) >> 5, (uint32_t)NJMAX);
+    // specialise on the number of live candidate slots (warp-uniform) so idle slots cost nothing
+    auto run = [&](auto tag) {
+      constexpr int NJ = decltype(tag)::value;
+      T x[NJ], y[NJ], z[NJ];
+      uint32_t l[NJ], t[NJ];
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) { x[q] = xj[q]; y[q] = yj[q]; z[q] = zj[q]; l[q] = lj[q]; t[q] = thr[q]; }
+      exact_tests<T, CMP, NJ>(home, r.m, x, y, z, l, t, c2, cons);
+    };
+    if constexpr (NJMAX == 1) {
+      run(IntTag<1>());
+    } else {
+      if (nj == 1) run(IntTag<1>());
+      else if (nj == 2) run(IntTag<2>());
+      else if (nj == 3) run(IntTag<3>());
+      else run(IntTag<4>());
+    }
+    cons.chunk_end();
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class T, int CMP, class Consumer>
-__global__ void __launch_bounds__(kPairThreads) pair_kernel(PairParams<T> p, typename Consumer::Args args) {
+// Prefilter loop (f64 grids, staged tiles): the same enumeration on the float4 tile-relative
+// coordinates rel[pos - plo]; `lo` / `hi` are the guard-band thresholds (prefilter_delta).
+template <int CMP, int NJ, class Consumer>
+__device__ __forceinline__ void prefilter_tests(const float4* __restrict__ home, uint32_t m, uint32_t hpos,
+                                                const float (&xj)[NJ], const float (&yj)[NJ],
+                                                const float (&zj)[NJ], const uint32_t (&jpos)[NJ],
+                                                const uint32_t (&thr)[NJ], float lo, float hi, Consumer& cons) {
+#pragma unroll 2
+  for (uint32_t i = 0; i < m; ++i) {
+    const float4 v = home[i];
+    bool maybe[NJ], sure[NJ];
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+      const float dx = v.x - xj[q], dy = v.y - yj[q], dz = v.z - zj[q];
+      const float dsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+      const bool in = i < thr[q];
+      maybe[q] = in && dsq <= hi;
+      sure[q] = in && dsq < lo;
+    }
+    cons.template maybe_n<CMP, NJ>(maybe, sure, hpos + i, jpos);
+  }
+}
+
+template <int CMP, class Consumer>
+__device__ __forceinline__ void process_cell_prefilter(const PairParams<double>& p, uint32_t c,
+                                                       const float4* __restrict__ rel, uint32_t plo,
+                                                       const uint32_t* __restrict__ csrb, float lo, float hi,
+                                                       Consumer& cons) {
+  CellRuns r;
+  if (!cell_runs(p, c, csrb, r)) return;
+  const unsigned lane = lane_id();
+  const float4* home = rel + (r.hb - plo);
+  for (uint32_t kb = 0; kb < r.K; kb += 32 * kMaxNJ) {
+    float xj[kMaxNJ], yj[kMaxNJ], zj[kMaxNJ];
+    uint32_t jpos[kMaxNJ], thr[kMaxNJ];
+#pragma unroll
+    for (int q = 0; q < kMaxNJ; ++q) {
+      const uint32_t k = kb + 32u * q + lane;
+      thr[q] = r.thr(k);
+      jpos[q] = r.pos(k) - plo;
+      if (kb + 32u * q < r.K) {
+        const float4 v = rel[jpos[q]];
+        xj[q] = v.x; yj[q] = v.y; zj[q] = v.z;
+      }
+    }
+    const uint32_t nj = min((r.K - kb + 31u) >> 5, (uint32_t)kMaxNJ);
+    auto run = [&](auto tag) {
+      constexpr int NJ = decltype(tag)::value;
+      float x[NJ], y[NJ], z[NJ];
+      uint32_t jp[NJ], t[NJ];
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) { x[q] = xj[q]; y[q] = yj[q]; z[q] = zj[q]; jp[q] = jpos[q]; t[q] = thr[q]; }
+      prefilter_tests<CMP, NJ>(home, r.m, r.hb - plo, x, y, z, jp, t, lo, hi, cons);
+    };
+    if (nj == 1) run(IntTag<1>());
+    else if (nj == 2) run(IntTag<2>());
+    else if (nj == 3) run(IntTag<3>());
+    else run(IntTag<4>());
+    cons.chunk_end();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class T, int CMP, class Consumer, bool PF>
+__global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(PairParams<T> p, typename Consumer::Args args) {
+  constexpr bool kCanPrefilter = PF && sizeof(T) == 8 && CMP != 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Rec<T>* s_rec = reinterpret_cast<Rec<T>*>(smem_raw);
-  uint32_t* s_csr = reinterpret_cast<uint32_t*>(s_rec + p.stage_recs);
+  float4* s_rel = reinterpret_cast<float4*>(s_rec + p.stage_recs);  // f64 + prefilter only
+  uint32_t* s_csr = reinterpret_cast<uint32_t*>(s_rel + ((kCanPrefilter && p.prefilter) ? p.stage_recs : 0u));
   unsigned char* s_cons = reinterpret_cast<unsigned char*>(s_csr + kStageCells + 4);
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ ConsumerSmem s_cs;
+  __shared__ uint32_t s_next;  // next unclaimed home cell of the tile (dynamic balance between warps)
 
   const int warp = threadIdx.x >> 5;
-  Consumer cons(args, &s_cs, s_cons + (size_t)warp * Consumer::kWarpSmemBytes);
+  const unsigned lane = lane_id();
+  const T c2 = keep_in_reg(p.c2);
+  Consumer cons(args, &s_cs, s_cons + (size_t)warp * Consumer::kWarpSmemBytes, c2);
 
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   uint32_t phase = 0;
 
-  const uint32_t halo = (uint32_t)p.w0 * (uint32_t)p.w1 + (uint32_t)p.w0 + 1u;
+  const uint32_t plane = (uint32_t)p.w0 * (uint32_t)p.w1;
+  const uint32_t halo = plane + (uint32_t)p.w0 + 1u;
   for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const uint32_t c0 = p.home_lo + tile * p.tile_cells;
     const uint32_t c1 = min(c0 + p.tile_cells, p.home_hi);
@@ -329,7 +730,25 @@ __global__ void __launch_bounds__(kPairThreads) pair_kernel(PairParams<T> p, typ
     const uint32_t np = phi - plo;
     const bool staged = np <= p.stage_recs && ncsr <= (uint32_t)kStageCells;
 
-    cons.tile_begin(tile);
+    // prefilter thresholds of this tile (warp-uniform)
+    bool pf = false;
+    float lo = 0.f, hi = 0.f;
+    if (kCanPrefilter && p.prefilter && staged && np > 0) {
+      const uint32_t nt = c1 - cl;  // cells spanned by the stage
+      const uint32_t sx = min((uint32_t)p.w0, nt);
+      const uint32_t sy = min((uint32_t)p.w1, (nt + (uint32_t)p.w0 - 1) / (uint32_t)p.w0 + 1);
+      const uint32_t sz = min((uint32_t)p.w2, (nt + plane - 1) / plane + 1);
+      const float R = (float)max(sx, max(sy, sz)) * (float)p.cell * 1.0001f;
+      const float delta = prefilter_delta(R / (float)p.fc);
+      if (delta < 0.25f) {
+        pf = true;
+        lo = __fmul_rd(__double2float_rd((double)c2), 1.0f - delta);
+        hi = __fmul_ru(__double2float_ru((double)c2), 1.0f + delta);
+      }
+    }
+
+    cons.tile_begin(tile, s_rec, pf);
+    if (threadIdx.x == 0) s_next = c0 + kPairWarps;
     if (staged) {
       if (threadIdx.x == 0 && np > 0) {
         const uint32_t bytes = np * (uint32_t)sizeof(Rec<T>);
@@ -337,19 +756,40 @@ __global__ void __launch_bounds__(kPairThreads) pair_kernel(PairParams<T> p, typ
         bulk_g2s(s_rec, p.sorted + plo, bytes, &s_bar);
       }
       for (uint32_t k = threadIdx.x; k < ncsr; k += kPairThreads) s_csr[k] = __ldg(p.csr + cl + k);
-      __syncthreads();
       if (np > 0) {
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
       }
-      for (uint32_t c = c0 + warp; c < c1; c += kPairWarps)
-        process_cell<T, CMP, true>(p, c, s_rec, plo, s_csr, cl, cons);
-    } else {
-      __syncthreads();
-      for (uint32_t c = c0 + warp; c < c1; c += kPairWarps)
-        process_cell<T, CMP, false>(p, c, p.sorted, 0u, p.csr, 0u, cons);
+      if constexpr (kCanPrefilter) {
+        if (pf) {
+          // tile-relative f32 coordinates; origin = the stage's first record
+          const double ox = s_rec[0].x, oy = s_rec[0].y, oz = s_rec[0].z;
+          for (uint32_t k = threadIdx.x; k < np; k += kPairThreads) {
+            double x, y, z;
+            uint32_t l;
+            load_part<false>(s_rec + k, x, y, z, l);
+            s_rel[k] = make_float4((float)(x - ox), (float)(y - oy), (float)(z - oz), 0.f);
+          }
+        }
+      }
     }
-    cons.tile_end(tile);  // ends with __syncthreads(): the stage buffers may be overwritten
+    __syncthreads();
+    // warps claim home cells one at a time: the first kPairWarps statically, the rest from s_next
+    for (uint32_t c = c0 + warp; c < c1;) {
+      // separate call sites so that the staged ones compile to shared-memory loads (LDS)
+      if constexpr (kCanPrefilter) {
+        if (pf) process_cell_prefilter<CMP>(p, c, s_rel, plo, s_csr - cl, lo, hi, cons);
+        else if (staged) process_cell<T, CMP>(p, c, s_rec - plo, s_csr - cl, c2, cons);
+        else process_cell<T, CMP>(p, c, p.sorted, p.csr, c2, cons);
+      } else {
+        if (staged) process_cell<T, CMP>(p, c, s_rec - plo, s_csr - cl, c2, cons);
+        else process_cell<T, CMP>(p, c, p.sorted, p.csr, c2, cons);
+      }
+      uint32_t nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&s_next, 1u);
+      c = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    cons.template tile_end<CMP>(tile);  // ends with __syncthreads(): the stage buffers may be overwritten
   }
   cons.finish();
 }

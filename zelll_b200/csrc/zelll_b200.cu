@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -37,6 +38,7 @@ struct DevBuf {
 };
 
 constexpr uint32_t kMaxBboxBlocks = 148 * 4;
+constexpr uint32_t kMaxPairCtasPerSm = 8;
 constexpr uint64_t kMaxDenseCells = (1ull << 31) - 16;  // uint32 cell ids, table of 4 B entries
 
 // small device scratch block, zeroed at creation; re-armed by the kernels / rebuild
@@ -478,12 +480,21 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
 struct PairPlan {
   uint32_t tile_cells, ntiles, stage_recs, blocks;
   size_t smem;
+  bool prefilter;
 };
 
 template <class T>
-PairPlan plan_pairs(const zb_grid* g, size_t warp_smem) {
+PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   PairPlan pl;
-  pl.stage_recs = sizeof(T) == 8 ? 2048u : 4096u;  // 64 KB of records -> 3 CTAs per SM
+  // f64 grids with a distance filter run staged tiles through the f32 prefilter (pair_kernels.cuh)
+  // (opt-in: measured at parity with the exact loop on the benchmark box)
+  pl.prefilter = sizeof(T) == 8 && cmp != ZB_CMP_NONE && getenv("ZB_PREFILTER") != nullptr;
+  const size_t rec_bytes = sizeof(Rec<T>) + (pl.prefilter ? sizeof(float4) : 0);
+  pl.stage_recs = sizeof(T) == 8 ? (pl.prefilter ? 1280u : 1536u) : 3072u;  // 48-60 KB of stage per CTA
+  if (const char* e = getenv("ZB_STAGE_RECS")) {     // tuning knob for experiments
+    const long v = atol(e);
+    if (v >= 64 && v <= 6144) pl.stage_recs = (uint32_t)v;
+  }
   const uint64_t plane = (g->ndim == 3) ? (uint64_t)g->wshape[0] * g->wshape[1] : 0;
   const uint64_t halo = plane + (uint64_t)g->wshape[0] + 1;
   const uint32_t nhome = g->home_hi - g->home_lo;
@@ -496,14 +507,25 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem) {
     if (room >= 8) tc = (uint32_t)room;
   }
   // enough tiles to balance the persistent grid
-  const uint32_t want_tiles = (uint32_t)g->sm_count * 3 * 4;
+  const uint32_t want_tiles = (uint32_t)g->sm_count * 4 * 4;
   if (nhome / std::max(tc, 1u) < want_tiles) tc = std::max<uint32_t>(8, (nhome + want_tiles - 1) / want_tiles);
   tc = std::max<uint32_t>(tc, 1);
   pl.tile_cells = tc;
   pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
-  pl.blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * 3));
-  pl.smem = (size_t)pl.stage_recs * sizeof(Rec<T>) + (kStageCells + 4) * sizeof(uint32_t) + kPairWarps * warp_smem;
+  pl.blocks = (uint32_t)g->sm_count * kMaxPairCtasPerSm;  // upper bound (buffers); the launch picks the real grid
+  pl.smem = (size_t)pl.stage_recs * rec_bytes + (kStageCells + 4) * sizeof(uint32_t) + kPairWarps * warp_smem;
   return pl;
+}
+
+// q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(n, mul): exact for every 32-bit n and d >= 1
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;  // ceil(log2 d)
+  f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l > 0 ? l - 1 : 0;
+  return f;
 }
 
 template <class T>
@@ -521,13 +543,23 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.stage_recs = pl.stage_recs;
   const T c = (T)filter_cutoff;
   p.c2 = c * c;  // cutoff.powi(2) in T (benches/lj.rs:85)
+  p.fc = c;
+  p.cell = (T)g->cutoff;
+  p.prefilter = pl.prefilter ? 1 : 0;
+  p.div0 = make_fastdiv((uint32_t)g->wshape[0]);
+  p.div1 = make_fastdiv((uint32_t)g->wshape[1]);
   return p;
 }
 
 template <class T, class Consumer>
-int launch_pairs(zb_grid* g, int cmp, const PairPlan& pl, const PairParams<T>& p, typename Consumer::Args args) {
+int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p, typename Consumer::Args args) {
   auto go = [&](auto kern) -> int {
     ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    // persistent grid: one wave of resident CTAs
+    int occ = 0;
+    ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPairThreads, pl.smem));
+    occ = std::max(1, std::min(occ, (int)kMaxPairCtasPerSm));
+    pl.blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * (uint32_t)occ));
     {
       StageSpan span(g, Consumer::kStage);
       kern<<<pl.blocks, kPairThreads, pl.smem, g->stream>>>(p, args);
@@ -536,10 +568,14 @@ int launch_pairs(zb_grid* g, int cmp, const PairPlan& pl, const PairParams<T>& p
     ZB_CUDA(cudaGetLastError());
     return ZB_OK;
   };
+  if constexpr (sizeof(T) == 8) {
+    if (pl.prefilter && cmp == ZB_CMP_LT) return go(pair_kernel<T, 1, Consumer, true>);
+    if (pl.prefilter && cmp == ZB_CMP_LE) return go(pair_kernel<T, 2, Consumer, true>);
+  }
   switch (cmp) {
-    case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer>);
-    case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer>);
-    case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer>);
+    case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer, false>);
+    case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer, false>);
+    case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer, false>);
   }
   return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
 }
@@ -555,8 +591,7 @@ int finalize(zb_grid* g, bool with_energy, uint32_t nblocks) {
 
 template <class T>
 int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* plan_out) {
-  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes);
-  if (plan_out) *plan_out = pl;
+  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, cmp);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   if (per_tile) ZB_TRY(reserve(g, g->tile_counts, ((size_t)pl.ntiles + 1) * 8));
   typename CountConsumer<T>::Args a;
@@ -565,12 +600,13 @@ int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* pla
   ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
   if (pl.ntiles) ZB_TRY((launch_pairs<T, CountConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
   ZB_TRY(finalize(g, false, pl.blocks));
+  if (plan_out) *plan_out = pl;
   return ZB_OK;
 }
 
 template <class T>
 int lj_impl(zb_grid* g, int cmp, double fc) {
-  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes);
+  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes, cmp);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   ZB_TRY(reserve(g, g->block_energy, (size_t)pl.blocks * 8));
   typename LjConsumer<T>::Args a;
@@ -592,8 +628,7 @@ int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev
   a.tile_offsets = static_cast<const unsigned long long*>(g->tile_offsets.p);
   a.out = out_dev;
   PairPlan pe = pl;
-  pe.smem = (size_t)pl.stage_recs * sizeof(Rec<T>) + (kStageCells + 4) * sizeof(uint32_t) +
-            kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
+  pe.smem = pl.smem - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
   if (pl.ntiles) ZB_TRY((launch_pairs<T, EmitConsumer<T>>(g, cmp, pe, pair_params<T>(g, pl, fc), a)));
   return ZB_OK;
 }
