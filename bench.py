@@ -24,7 +24,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -53,42 +52,56 @@ def _peaks():
 # ---------------------------------------------------------------------------------------------
 # clocks during the timed region
 class ClockSampler:
+    """`nvidia-smi -lms` in the background while the timed region runs (B200_PROFILING.md clocks line)."""
+
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self._stop = threading.Event()
-        self._thr = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+        self.proc = None
 
     def start(self):
-        self._thr = threading.Thread(target=self._run, daemon=True)
-        self._thr.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self) -> dict:
-        self._stop.set()
-        if self._thr:
-            self._thr.join(timeout=10)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=10)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for line in out.splitlines():
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 7:
+                    rows.append(parts)
+
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+
+        sm = [num(r[0]) for r in rows if num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if num(r[2]) is not None]
+        # "under load" = the samples in the upper half of the power range
+        load = sm
+        if pw and len(pw) == len(sm) and max(pw) > min(pw):
+            thr = 0.5 * (max(pw) + min(pw))
+            load = [c for c, w in zip(sm, pw) if w >= thr] or sm
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -116,6 +116,16 @@ int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6);
 int zb_layer_of(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double cutoff, int axis,
                 int32_t* out);
 
+/* Slab-local input of the sharded host: checks that all n particles lie in layers [z_begin, z_end)
+ * of the slab axis (*out_of_slab = 1 otherwise) and compacts the particles of the top layer
+ * z_end - 1 -- the next rank's lower halo -- into rows {x, y, z, label_offset + index} of the grid's
+ * dtype at halo_rows[1 .. 1 + *n_top) (DEVICE memory, capacity cap_rows + 1 rows of 4 values; row 0
+ * is left to the caller, who stores the count there before sending the block over NVLink).
+ * The label is stored as raw bits in the 4th value (reinterpret as uint32 / int64, not a number). */
+int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double cutoff,
+                      int64_t z_begin, int64_t z_end, uint32_t label_offset, void* halo_rows,
+                      uint64_t cap_rows, uint64_t* n_top, int* out_of_slab);
+
 /* -- inspection ---------------------------------------------------------------------------- */
 
 /* CellGrid::info() (src/cellgrid.rs:346-348) */

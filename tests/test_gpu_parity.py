@@ -373,3 +373,24 @@ def test_full_size_properties(zb, dtype):
     cg.rebuild(pts[perm])
     e3, m3 = cg.lj_energy(10.0, "lt", return_pairs=True)
     assert (m3, e3) == (m2, e3) and abs(e3 - e2) <= 1e-13 * abs(e2)
+
+
+# ---------------------------------------------------------------------------------------------
+# real multi-GPU run (NCCL) when the box has more than one GPU; the host logic is covered on CPU by
+# tests/test_sharded_cpu.py (gloo) and the per-rank engine by test_sharded_union_equals_single_grid
+def test_distributed_nccl_matches_single_gpu():
+    import subprocess
+    import sys
+
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", "scripts/dist_check.py", "200000"]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MISMATCH" not in out.stdout

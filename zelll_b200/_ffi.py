@@ -51,6 +51,8 @@ SIGNATURES = {
     "zb_grid_rebuild_sharded": (_int, [_vp, _vp, _u64, _vp, _dp, _dp, _dp, _i64, _i64]),
     "zb_aabb": (_int, [_vp, _vp, _u64, _dp]),
     "zb_layer_of": (_int, [_vp, _vp, _u64, _dbl, _dbl, _int, _vp]),
+    "zb_slab_top_layer": (_int, [_vp, _vp, _u64, _dbl, _dbl, _i64, _i64, C.c_uint32, _vp, _u64, _u64p,
+                                 C.POINTER(C.c_int)]),
     "zb_grid_info": (_int, [_vp, C.POINTER(ZbInfo)]),
     "zb_grid_keys": (_int, [_vp, _vp]),
     "zb_grid_neighbor_indices": (_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

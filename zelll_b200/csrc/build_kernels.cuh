@@ -388,6 +388,45 @@ __global__ void layer_kernel(const T* __restrict__ xyz, uint32_t n, int ndim, in
   out[i] = cell_coord(__ldg(xyz + (uint64_t)i * ndim + axis), inf, cutoff);
 }
 
+template <class T>
+__device__ __forceinline__ T label_bits(uint32_t label);
+template <>
+__device__ __forceinline__ float label_bits<float>(uint32_t label) { return __uint_as_float(label); }
+template <>
+__device__ __forceinline__ double label_bits<double>(uint32_t label) { return __longlong_as_double((long long)label); }
+
+// Slab-local input check + halo extraction of the sharded host: every particle must
+// lie in layers [z_begin, z_end) of the slab axis (else *bad = 1); the particles of the TOP layer
+// z_end - 1 -- the lower halo of the next rank -- are compacted into rows {x, y, z, label} of
+// out[1..] (order unspecified), their number accumulates in *count.
+template <class T, int NDIM>
+__global__ void __launch_bounds__(256) slab_top_kernel(const T* __restrict__ xyz, uint32_t n, T inf, T cutoff,
+                                                       int z_begin, int z_end, uint32_t label_offset,
+                                                       T* __restrict__ out, uint32_t cap,
+                                                       uint32_t* __restrict__ count, int* __restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool top = false;
+  T x = T(0), y = T(0), z = T(0);
+  if (i < n) {
+    load_point<T, NDIM>(xyz, i, x, y, z);
+    const int layer = cell_coord(NDIM == 3 ? z : y, inf, cutoff);
+    if (layer < z_begin || layer >= z_end) *bad = 1;
+    top = layer == z_end - 1;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, top);
+  if (b == 0) return;
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(count, (uint32_t)__popc(b));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (top) {
+    const uint32_t slot = base + __popc(b & lanemask_lt());
+    if (slot < cap) {
+      T* row = out + (uint64_t)(slot + 1) * 4;
+      row[0] = x; row[1] = y; row[2] = z; row[3] = label_bits<T>(label_offset + i);
+    }
+  }
+}
+
 // cell_storage(): unpack records into labels / packed coordinates
 template <class T, int NDIM>
 __global__ void unpack_kernel(const Rec<T>* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ labels,

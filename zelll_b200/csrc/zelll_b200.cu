@@ -797,6 +797,57 @@ int zb_layer_of(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double
   return ZB_OK;
 }
 
+int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double cutoff, int64_t z_begin,
+                      int64_t z_end, uint32_t label_offset, void* halo_rows, uint64_t cap_rows, uint64_t* n_top,
+                      int* out_of_slab) {
+  ZB_TRY(enter(g));
+  if (!n_top || !out_of_slab) return fail(g, ZB_ERR_BAD_ARG, "n_top / out_of_slab is NULL");
+  *n_top = 0;
+  *out_of_slab = 0;
+  if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
+  if (n == 0) return ZB_OK;
+  if (!xyz || !halo_rows || !is_device_ptr(halo_rows)) return fail(g, ZB_ERR_BAD_ARG, "halo_rows must be device memory");
+  const void* dev = nullptr;
+  ZB_TRY(stage_input(g, xyz, n, &dev));
+  ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 3 * sizeof(uint32_t), g->stream));  // counter, -, flags
+  const uint32_t blocks = (uint32_t)((n + 255) / 256);
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(cap_rows, 0xfffffff0ull);
+  if (g->dtype == ZB_F32) {
+    if (g->ndim == 3)
+      slab_top_kernel<float, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const float*>(dev), (uint32_t)n, (float)inf_axis,
+                                                               (float)cutoff, (int)z_begin, (int)z_end, label_offset,
+                                                               static_cast<float*>(halo_rows), cap,
+                                                               &g->misc->tile_counter, &g->misc->flags);
+    else
+      slab_top_kernel<float, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const float*>(dev), (uint32_t)n, (float)inf_axis,
+                                                               (float)cutoff, (int)z_begin, (int)z_end, label_offset,
+                                                               static_cast<float*>(halo_rows), cap,
+                                                               &g->misc->tile_counter, &g->misc->flags);
+  } else {
+    if (g->ndim == 3)
+      slab_top_kernel<double, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const double*>(dev), (uint32_t)n, inf_axis, cutoff,
+                                                                (int)z_begin, (int)z_end, label_offset,
+                                                                static_cast<double*>(halo_rows), cap,
+                                                                &g->misc->tile_counter, &g->misc->flags);
+    else
+      slab_top_kernel<double, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const double*>(dev), (uint32_t)n, inf_axis, cutoff,
+                                                                (int)z_begin, (int)z_end, label_offset,
+                                                                static_cast<double*>(halo_rows), cap,
+                                                                &g->misc->tile_counter, &g->misc->flags);
+  }
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->tile_counter, &g->misc->tile_counter, 3 * sizeof(uint32_t),
+                          cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  *n_top = g->h_misc->tile_counter;
+  *out_of_slab = g->h_misc->flags & 1;
+  if (*n_top > cap_rows)
+    return fail(g, ZB_ERR_CAPACITY, "top layer holds %llu particles, halo buffer %llu rows", (unsigned long long)*n_top,
+                (unsigned long long)cap_rows);
+  return ZB_OK;
+}
+
 int zb_grid_info(zb_grid* g, zb_info* out) {
   if (!g || !out) return ZB_ERR_BAD_ARG;
   memset(out, 0, sizeof *out);

@@ -74,6 +74,19 @@ class ShardedCellGrid(CellGrid):
             return torch.from_numpy(out)
         return out
 
+    def slab_top_layer(self, points, inf_axis: float, cutoff: float, z_begin: int, z_end: int, label_offset: int,
+                       halo_rows, cap_rows: int) -> int:
+        """Check slab-locality of `points` and compact their top layer into halo_rows[1:] (device tensor of
+        shape [cap_rows + 1, 4]); returns the number of rows written."""
+        ptr, n, keep, _ = self._marshal(points)
+        n_top, bad = C.c_uint64(0), C.c_int(0)
+        self._check(self._lib.zb_slab_top_layer(self._h, ptr, n, float(inf_axis), float(cutoff), int(z_begin), int(z_end),
+                                                int(label_offset) & 0xFFFFFFFF, halo_rows.data_ptr(), int(cap_rows),
+                                                C.byref(n_top), C.byref(bad)))
+        if bad.value:
+            raise ValueError("rebuild_slab_local: input is not slab-local; use rebuild()")
+        return int(n_top.value)
+
     def rebuild_local(self, points, labels, cutoff, inf, sup, z_begin: int, z_end: int) -> None:
         ptr, n, keep, _ = self._marshal(points)
         lab_keep, lptr = None, None
@@ -119,6 +132,8 @@ class DistributedCellGrid:
         self.z_begin = self.z_end = 0
         self.n_home = 0
         self.n_halo = 0
+        self._halo_send = self._halo_recv = None
+        self._labels, self._labels_key = None, None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _tdtype(self):
@@ -178,10 +193,11 @@ class DistributedCellGrid:
         dist.all_to_all_single(recv_lab, send_lab, output_split_sizes=rcounts, input_split_sizes=counts, group=self.group)
         self._finish(recv_pts, recv_lab)
 
-    def rebuild_slab_local(self, buf, n_local: int, cutoff: float, label_offset: int, box=None):
+    def rebuild_slab_local(self, buf, n_local: int, cutoff: float, label_offset: int, box=None, halo_cap: int = 8192):
         """Fast path: rank r already holds exactly the particles of its own layers in buf[:n_local]
         (generated per slab, or presorted and split at layer boundaries); buf has spare rows at the
-        tail that receive the lower halo layer from rank r-1 -- the only NVLink traffic.
+        tail that receive the lower halo layer from rank r-1 -- the only NVLink traffic: ONE
+        fixed-size send/recv of {count; x, y, z, label} rows per neighbour pair.
         `box` = (inf, sup) skips the bounding-box all-reduce when the global box is known."""
         torch, dist = self._torch, self._dist
         points = buf[:n_local]
@@ -192,40 +208,39 @@ class DistributedCellGrid:
             self.cutoff = float(self.dtype.type(cutoff))
             self.shape = grid_shape(self.inf, self.sup, cutoff, self.dtype)
             self.z_begin, self.z_end = slab_bounds(self.shape[-1], self.world, self.rank)
-        layer = torch.as_tensor(self.engine.layer_of(points, float(self.inf[-1]), self.cutoff)).to(points.device)
-        if n_local and (int(layer.min()) < self.z_begin or int(layer.max()) >= self.z_end):
-            raise ValueError("rebuild_slab_local: input is not slab-local; use rebuild()")
-        top = torch.nonzero(layer == self.z_end - 1).reshape(-1)
         up, down = self.rank + 1, self.rank - 1
-        n_send = torch.tensor([int(top.numel())], dtype=torch.int64, device=self.comm_device)
-        n_recv = torch.zeros(1, dtype=torch.int64, device=self.comm_device)
+        if self._halo_send is None or self._halo_send.shape[0] != halo_cap + 1 or self._halo_send.device != buf.device:
+            self._halo_send = torch.zeros((halo_cap + 1, 4), dtype=buf.dtype, device=buf.device)
+            self._halo_recv = torch.zeros((halo_cap + 1, 4), dtype=buf.dtype, device=buf.device)
+        # top layer of this slab -> halo block (one engine kernel; also verifies slab-locality)
+        n_top = self.engine.slab_top_layer(points, float(self.inf[-1]), self.cutoff, self.z_begin, self.z_end,
+                                           label_offset, self._halo_send, halo_cap)
+        self._halo_send[0, 0] = float(n_top)
         ops = []
         if up < self.world:
-            ops.append(dist.P2POp(dist.isend, n_send, up, group=self.group))
+            ops.append(dist.P2POp(dist.isend, self._halo_send, up, group=self.group))
         if down >= 0:
-            ops.append(dist.P2POp(dist.irecv, n_recv, down, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, self._halo_recv, down, group=self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        n_halo = int(n_recv.item())
+        n_halo = int(self._halo_recv[0, 0].item()) if down >= 0 else 0
         if n_local + n_halo > buf.shape[0]:
             raise ValueError(f"halo of {n_halo} rows does not fit the {buf.shape[0] - n_local} spare rows of buf")
-        send_pts = points[top].contiguous()
-        send_lab = (top + label_offset).to(torch.int64)
-        recv_lab = torch.empty(n_halo, dtype=torch.int64, device=points.device)
-        ops = []
-        if up < self.world and top.numel():
-            ops += [dist.P2POp(dist.isend, send_pts, up, group=self.group),
-                    dist.P2POp(dist.isend, send_lab, up, group=self.group)]
-        if down >= 0 and n_halo:
-            ops += [dist.P2POp(dist.irecv, buf[n_local:n_local + n_halo], down, group=self.group),
-                    dist.P2POp(dist.irecv, recv_lab, down, group=self.group)]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        labels = torch.cat([torch.arange(label_offset, label_offset + n_local, dtype=torch.int64, device=points.device),
-                            recv_lab])
-        self._finish(buf[:n_local + n_halo], labels)
+        # persistent label array: local labels are written once, only the halo tail changes per step
+        key = (int(buf.shape[0]), int(n_local), int(label_offset), str(buf.device))
+        if self._labels_key != key:
+            self._labels = torch.empty(buf.shape[0], dtype=torch.int32, device=buf.device)
+            self._labels[:n_local] = (torch.arange(n_local, dtype=torch.int64, device=buf.device) + label_offset).to(torch.int32)
+            self._labels_key = key
+        if n_halo:
+            rows = self._halo_recv[1:1 + n_halo]
+            buf[n_local:n_local + n_halo] = rows[:, :3]
+            bits = rows[:, 3].contiguous().view(torch.int64 if buf.dtype == torch.float64 else torch.int32)
+            self._labels[n_local:n_local + n_halo] = bits.to(torch.int32)
+        self.n_total_local = n_local + n_halo
+        self.engine.rebuild_local(buf[:n_local + n_halo], self._labels[:n_local + n_halo], self.cutoff, self.inf, self.sup,
+                                  self.z_begin, self.z_end)
 
     def _finish(self, pts, labels):
         torch = self._torch
@@ -247,10 +262,9 @@ class DistributedCellGrid:
 
     def lj_energy(self, cutoff: Optional[float] = None, cmp="lt", return_pairs: bool = False):
         e, m = self.engine.lj_energy(self.cutoff if cutoff is None else cutoff, cmp, return_pairs=True)
-        e_all = self._allreduce_sum([e], self._torch.float64)[0]
-        if not return_pairs:
-            return e_all
-        return e_all, int(self._allreduce_sum([m], self._torch.int64)[0])
+        # one all-reduce for both values (the pair count is exact in f64 below 2^53)
+        e_all, m_all = self._allreduce_sum([e, float(m)], self._torch.float64)
+        return (e_all, int(m_all)) if return_pairs else e_all
 
     def local_particle_pairs(self, cutoff: Optional[float] = None, cmp="none") -> np.ndarray:
         """This rank's shard of the pair list (global labels); the list stays sharded."""
