@@ -280,11 +280,12 @@ def run_ours(args):
         return float(t.item()), out, engine.launch_count - launches0, stages
 
     # ---- warm-up, then the timed region (device-resident inputs) -------------------------------
-    for _ in range(warmup):
-        energy, pairs = step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # nvidia-smi needs ~0.2 s to come up: start it ahead of the warm-up
+        time.sleep(0.5)
+    for _ in range(warmup):
+        energy, pairs = step_resident()
     ms_total, (energy, pairs), launches, stages = timed(step_resident, steps, profile=True)
     # ---- the same step end to end from pinned host memory --------------------------------------
     for _ in range(2):

@@ -107,7 +107,8 @@ int zb_grid_rebuild_sharded(zb_grid* g, const void* xyz, uint64_t n, const uint3
                             int64_t z_begin, int64_t z_end);
 
 /* Aabb::from_particles alone (util.rs:35-52): out[0..ndim) = inf, out[3..3+ndim) = sup as f64.
- * Used by the sharded host to all-reduce the global box before zb_grid_rebuild_sharded. */
+ * Used by the sharded host to all-reduce the global box before zb_grid_rebuild_sharded; with a
+ * DEVICE out6 the call is asynchronous and the box can be all-reduced without a host round trip. */
 int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6);
 
 /* Cell coordinate of every particle along one axis, floor((x[axis] - inf_axis) / cutoff) as i32 in
@@ -120,8 +121,10 @@ int zb_layer_of(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double
  * of the slab axis (*out_of_slab = 1 otherwise) and compacts the particles of the top layer
  * z_end - 1 -- the next rank's lower halo -- into rows {x, y, z, label_offset + index} of the grid's
  * dtype at halo_rows[1 .. 1 + *n_top) (DEVICE memory, capacity cap_rows + 1 rows of 4 values; row 0
- * is left to the caller, who stores the count there before sending the block over NVLink).
- * The label is stored as raw bits in the 4th value (reinterpret as uint32 / int64, not a number). */
+ * receives the row count as a number, so the block can be sent over NVLink as it is).  The label
+ * is stored as raw bits in the 4th value (reinterpret as uint32 / int64, not a number).
+ * With n_top == NULL and out_of_slab == NULL the call is asynchronous: the slab check is then
+ * reported by the next zb_grid_rebuild_sharded on this handle (ZB_ERR_OUT_OF_WINDOW). */
 int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, double cutoff,
                       int64_t z_begin, int64_t z_end, uint32_t label_offset, void* halo_rows,
                       uint64_t cap_rows, uint64_t* n_top, int* out_of_slab);

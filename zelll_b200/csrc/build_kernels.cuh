@@ -379,6 +379,19 @@ __global__ void keys_changed_kernel(const int32_t* __restrict__ old_keys, uint32
   if (o != new_keys[i]) *changed = 1;
 }
 
+// bbox result (T) -> 6 doubles in device memory, for all-reducing the box without a host round trip
+template <class T>
+__global__ void widen6_kernel(const T* __restrict__ in6, double* __restrict__ out6, int ndim) {
+  const int k = threadIdx.x;
+  if (k < 6) out6[k] = (k % 3) < ndim ? (double)in6[k] : 0.0;
+}
+
+// halo block header: row 0, value 0 = number of rows that follow (as a number, not as bits)
+template <class T>
+__global__ void halo_header_kernel(const uint32_t* __restrict__ count, uint32_t cap, T* __restrict__ rows) {
+  rows[0] = (T)min(*count, cap + 1u);  // cap + 1 signals overflow to the receiver
+}
+
 // per-axis cell coordinate of packed input particles (slab assignment of the sharded host)
 template <class T>
 __global__ void layer_kernel(const T* __restrict__ xyz, uint32_t n, int ndim, int axis, T inf, T cutoff,

@@ -52,6 +52,8 @@ struct Misc {
   double out6[6];          // bbox result (T-typed, stored in the leading bytes)
   double energy;           // finalize_kernel
   unsigned long long pair_total;
+  uint32_t slab_count;     // slab_top_kernel: rows in the halo block
+  uint32_t slab_flag;      // slab_top_kernel: bit0 = a particle outside the slab
 };
 
 }  // namespace
@@ -80,6 +82,7 @@ struct zb_grid {
   uint32_t home_lo = 0, home_hi = 1;
   bool sharded = false;
   bool track_keys = false;
+  bool slab_check_pending = false;  // an asynchronous zb_slab_top_layer awaits its verdict
   int keys_changed = -1;
   uint64_t n_keys_old = 0;
 
@@ -459,11 +462,20 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   // flags / non-empty count come back with the info read (one small sync copy)
   ZB_CUDA(cudaMemcpyAsync(&g->h_misc->tile_counter, &g->misc->tile_counter, 3 * sizeof(uint32_t),
                           cudaMemcpyDeviceToHost, g->stream));
+  const bool slab_check = sharded && g->slab_check_pending;
+  if (slab_check)
+    ZB_CUDA(cudaMemcpyAsync(&g->h_misc->slab_count, &g->misc->slab_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            g->stream));
   if (g->track_keys && !sharded) ZB_TRY(track_keys<T>(g));
   if (g->track_keys && !sharded)
     ZB_CUDA(cudaMemcpyAsync(&g->h_misc->keys_changed, &g->misc->keys_changed, sizeof(int), cudaMemcpyDeviceToHost,
                             g->stream));
   ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (slab_check) {
+    g->slab_check_pending = false;
+    if (g->h_misc->slab_flag & 1u)
+      return fail(g, ZB_ERR_OUT_OF_WINDOW, "slab-local input held a particle outside its own layers");
+  }
   if (g->h_misc->flags & 1)
     return fail(g, sharded ? ZB_ERR_OUT_OF_WINDOW : ZB_ERR_BAD_ARG,
                 sharded ? "a particle lies outside the imposed box / slab window"
@@ -750,19 +762,29 @@ int zb_grid_rebuild_sharded(zb_grid* g, const void* xyz, uint64_t n, const uint3
 int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6) {
   ZB_TRY(enter(g));
   if (!out6) return fail(g, ZB_ERR_BAD_ARG, "out6 is NULL");
-  for (int d = 0; d < 6; ++d) out6[d] = 0.0;
-  if (n == 0) return ZB_OK;
+  const bool dev_out = is_device_ptr(out6);
+  if (n == 0) {
+    if (dev_out) ZB_CUDA(cudaMemsetAsync(out6, 0, 6 * sizeof(double), g->stream));
+    else for (int d = 0; d < 6; ++d) out6[d] = 0.0;
+    return ZB_OK;
+  }
   if (!xyz) return fail(g, ZB_ERR_BAD_ARG, "xyz is NULL");
   const void* dev = nullptr;
   ZB_TRY(stage_input(g, xyz, n, &dev));
-  double o[6];
-  if (g->dtype == ZB_F32) {
-    ZB_TRY(launch_bbox<float>(g, static_cast<const float*>(dev), n));
-    ZB_TRY(fetch_bbox<float>(g, o));
-  } else {
-    ZB_TRY(launch_bbox<double>(g, static_cast<const double*>(dev), n));
-    ZB_TRY(fetch_bbox<double>(g, o));
+  if (g->dtype == ZB_F32) ZB_TRY(launch_bbox<float>(g, static_cast<const float*>(dev), n));
+  else ZB_TRY(launch_bbox<double>(g, static_cast<const double*>(dev), n));
+  if (dev_out) {
+    // stays on the device (asynchronous): the sharded host all-reduces it in place
+    if (g->dtype == ZB_F32) widen6_kernel<float><<<1, 32, 0, g->stream>>>(reinterpret_cast<const float*>(g->misc->out6), out6, g->ndim);
+    else widen6_kernel<double><<<1, 32, 0, g->stream>>>(reinterpret_cast<const double*>(g->misc->out6), out6, g->ndim);
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    return ZB_OK;
   }
+  double o[6];
+  if (g->dtype == ZB_F32) ZB_TRY(fetch_bbox<float>(g, o));
+  else ZB_TRY(fetch_bbox<double>(g, o));
+  for (int d = 0; d < 6; ++d) out6[d] = 0.0;
   for (int d = 0; d < g->ndim; ++d) {
     out6[d] = o[d];
     out6[3 + d] = o[3 + d];
@@ -801,47 +823,58 @@ int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, 
                       int64_t z_end, uint32_t label_offset, void* halo_rows, uint64_t cap_rows, uint64_t* n_top,
                       int* out_of_slab) {
   ZB_TRY(enter(g));
-  if (!n_top || !out_of_slab) return fail(g, ZB_ERR_BAD_ARG, "n_top / out_of_slab is NULL");
-  *n_top = 0;
-  *out_of_slab = 0;
+  const bool async = n_top == nullptr && out_of_slab == nullptr;
+  if (!async && (!n_top || !out_of_slab)) return fail(g, ZB_ERR_BAD_ARG, "n_top and out_of_slab go together");
+  if (!async) {
+    *n_top = 0;
+    *out_of_slab = 0;
+  }
   if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
-  if (n == 0) return ZB_OK;
-  if (!xyz || !halo_rows || !is_device_ptr(halo_rows)) return fail(g, ZB_ERR_BAD_ARG, "halo_rows must be device memory");
+  if (!halo_rows || !is_device_ptr(halo_rows)) return fail(g, ZB_ERR_BAD_ARG, "halo_rows must be device memory");
+  if (n > 0 && !xyz) return fail(g, ZB_ERR_BAD_ARG, "xyz is NULL");
   const void* dev = nullptr;
   ZB_TRY(stage_input(g, xyz, n, &dev));
-  ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 3 * sizeof(uint32_t), g->stream));  // counter, -, flags
+  // slab_count / slab_flag live apart from the rebuild's counters: the flag is read by the NEXT sharded rebuild
+  ZB_CUDA(cudaMemsetAsync(&g->misc->slab_count, 0, 2 * sizeof(uint32_t), g->stream));
   const uint32_t blocks = (uint32_t)((n + 255) / 256);
   const uint32_t cap = (uint32_t)std::min<uint64_t>(cap_rows, 0xfffffff0ull);
-  if (g->dtype == ZB_F32) {
-    if (g->ndim == 3)
-      slab_top_kernel<float, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const float*>(dev), (uint32_t)n, (float)inf_axis,
-                                                               (float)cutoff, (int)z_begin, (int)z_end, label_offset,
-                                                               static_cast<float*>(halo_rows), cap,
-                                                               &g->misc->tile_counter, &g->misc->flags);
-    else
-      slab_top_kernel<float, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const float*>(dev), (uint32_t)n, (float)inf_axis,
-                                                               (float)cutoff, (int)z_begin, (int)z_end, label_offset,
-                                                               static_cast<float*>(halo_rows), cap,
-                                                               &g->misc->tile_counter, &g->misc->flags);
-  } else {
-    if (g->ndim == 3)
-      slab_top_kernel<double, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const double*>(dev), (uint32_t)n, inf_axis, cutoff,
-                                                                (int)z_begin, (int)z_end, label_offset,
-                                                                static_cast<double*>(halo_rows), cap,
-                                                                &g->misc->tile_counter, &g->misc->flags);
-    else
-      slab_top_kernel<double, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const double*>(dev), (uint32_t)n, inf_axis, cutoff,
-                                                                (int)z_begin, (int)z_end, label_offset,
-                                                                static_cast<double*>(halo_rows), cap,
-                                                                &g->misc->tile_counter, &g->misc->flags);
+  uint32_t* cnt = &g->misc->slab_count;
+  int* bad = reinterpret_cast<int*>(&g->misc->slab_flag);
+  if (n > 0) {
+    if (g->dtype == ZB_F32) {
+      auto* x = static_cast<const float*>(dev);
+      auto* o = static_cast<float*>(halo_rows);
+      if (g->ndim == 3)
+        slab_top_kernel<float, 3><<<blocks, 256, 0, g->stream>>>(x, (uint32_t)n, (float)inf_axis, (float)cutoff, (int)z_begin,
+                                                                 (int)z_end, label_offset, o, cap, cnt, bad);
+      else
+        slab_top_kernel<float, 2><<<blocks, 256, 0, g->stream>>>(x, (uint32_t)n, (float)inf_axis, (float)cutoff, (int)z_begin,
+                                                                 (int)z_end, label_offset, o, cap, cnt, bad);
+    } else {
+      auto* x = static_cast<const double*>(dev);
+      auto* o = static_cast<double*>(halo_rows);
+      if (g->ndim == 3)
+        slab_top_kernel<double, 3><<<blocks, 256, 0, g->stream>>>(x, (uint32_t)n, inf_axis, cutoff, (int)z_begin, (int)z_end,
+                                                                  label_offset, o, cap, cnt, bad);
+      else
+        slab_top_kernel<double, 2><<<blocks, 256, 0, g->stream>>>(x, (uint32_t)n, inf_axis, cutoff, (int)z_begin, (int)z_end,
+                                                                  label_offset, o, cap, cnt, bad);
+    }
+    g->launches++;
   }
+  // the block header (row 0) carries the row count to the receiver
+  if (g->dtype == ZB_F32) halo_header_kernel<float><<<1, 1, 0, g->stream>>>(cnt, cap, static_cast<float*>(halo_rows));
+  else halo_header_kernel<double><<<1, 1, 0, g->stream>>>(cnt, cap, static_cast<double*>(halo_rows));
   g->launches++;
   ZB_CUDA(cudaGetLastError());
-  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->tile_counter, &g->misc->tile_counter, 3 * sizeof(uint32_t),
-                          cudaMemcpyDeviceToHost, g->stream));
+  g->slab_check_pending = true;
+  if (async) return ZB_OK;
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->slab_count, &g->misc->slab_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          g->stream));
   ZB_CUDA(cudaStreamSynchronize(g->stream));
-  *n_top = g->h_misc->tile_counter;
-  *out_of_slab = g->h_misc->flags & 1;
+  g->slab_check_pending = false;
+  *n_top = g->h_misc->slab_count;
+  *out_of_slab = (int)(g->h_misc->slab_flag & 1u);
   if (*n_top > cap_rows)
     return fail(g, ZB_ERR_CAPACITY, "top layer holds %llu particles, halo buffer %llu rows", (unsigned long long)*n_top,
                 (unsigned long long)cap_rows);

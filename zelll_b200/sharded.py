@@ -57,6 +57,22 @@ class ShardedCellGrid(CellGrid):
             return np.full(nd, np.inf), np.full(nd, -np.inf)
         return np.array(out[0:nd]), np.array(out[3:3 + nd])
 
+    def local_aabb_into(self, points, out6) -> None:
+        """Asynchronous: (inf xyz, sup xyz) as 6 doubles into the CUDA tensor `out6` (+-inf when empty)."""
+        ptr, n, keep, _ = self._marshal(points)
+        if n == 0:
+            out6[:3] = float("inf")
+            out6[3:] = float("-inf")
+            return
+        self._check(self._lib.zb_aabb(self._h, ptr, n, C.cast(out6.data_ptr(), C.POINTER(C.c_double))))
+        if self.ndim < 3:
+            out6[self.ndim:3] = float("inf")
+            out6[3 + self.ndim:] = float("-inf")
+
+    def lj_energy_into(self, cutoff: float, cmp, energy_out, pairs_out) -> None:
+        """Asynchronous fused LJ pass: energy (f64[1]) and kept pairs (int64[1]) stay on the device."""
+        self._check(self._lib.zb_grid_lj_energy(self._h, CMP[cmp], float(cutoff), energy_out.data_ptr(), pairs_out.data_ptr()))
+
     def layer_of(self, points, inf_axis: float, cutoff: float, axis: Optional[int] = None):
         axis = self.ndim - 1 if axis is None else axis
         ptr, n, keep, _ = self._marshal(points)
@@ -79,13 +95,14 @@ class ShardedCellGrid(CellGrid):
         """Check slab-locality of `points` and compact their top layer into halo_rows[1:] (device tensor of
         shape [cap_rows + 1, 4]); returns the number of rows written."""
         ptr, n, keep, _ = self._marshal(points)
-        n_top, bad = C.c_uint64(0), C.c_int(0)
-        self._check(self._lib.zb_slab_top_layer(self._h, ptr, n, float(inf_axis), float(cutoff), int(z_begin), int(z_end),
-                                                int(label_offset) & 0xFFFFFFFF, halo_rows.data_ptr(), int(cap_rows),
-                                                C.byref(n_top), C.byref(bad)))
-        if bad.value:
-            raise ValueError("rebuild_slab_local: input is not slab-local; use rebuild()")
-        return int(n_top.value)
+        if halo_rows.is_cuda:
+            # asynchronous: the row count travels in the block header, the slab check is reported by
+            # the rebuild that follows
+            self._check(self._lib.zb_slab_top_layer(self._h, ptr, n, float(inf_axis), float(cutoff), int(z_begin),
+                                                    int(z_end), int(label_offset) & 0xFFFFFFFF, halo_rows.data_ptr(),
+                                                    int(cap_rows), None, None))
+            return -1
+        raise ValueError("halo_rows must be a CUDA tensor")
 
     def rebuild_local(self, points, labels, cutoff, inf, sup, z_begin: int, z_end: int) -> None:
         ptr, n, keep, _ = self._marshal(points)
@@ -134,6 +151,8 @@ class DistributedCellGrid:
         self.n_halo = 0
         self._halo_send = self._halo_recv = None
         self._labels, self._labels_key = None, None
+        self._box6 = None
+        self._red = self._red_pairs = None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _tdtype(self):
@@ -141,13 +160,23 @@ class DistributedCellGrid:
 
     def _global_box(self, points, cutoff):
         torch, dist = self._torch, self._dist
-        lo, hi = self.engine.local_aabb(points)
-        buf = torch.tensor(np.concatenate([-np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)]),
-                           dtype=torch.float64, device=self.comm_device)
-        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)  # max(-inf_d) = -min(inf_d)
-        buf = buf.cpu().numpy()
         nd = self.ndim
-        inf, sup = -buf[:nd], buf[nd:]
+        if hasattr(self.engine, "local_aabb_into") and getattr(points, "is_cuda", False):
+            # device path: bbox kernel -> negate inf -> all-reduce(max) -> ONE host read
+            if self._box6 is None:
+                self._box6 = torch.empty(6, dtype=torch.float64, device=points.device)
+            self.engine.local_aabb_into(points, self._box6)
+            self._box6[:3].neg_()
+            dist.all_reduce(self._box6, op=dist.ReduceOp.MAX, group=self.group)
+            b = self._box6.cpu().numpy()
+            inf, sup = -b[:nd], b[3:3 + nd]
+        else:
+            lo, hi = self.engine.local_aabb(points)
+            buf = torch.tensor(np.concatenate([-np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)]),
+                               dtype=torch.float64, device=self.comm_device)
+            dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)  # max(-inf_d) = -min(inf_d)
+            buf = buf.cpu().numpy()
+            inf, sup = -buf[:nd], buf[nd:]
         if not np.all(np.isfinite(inf)):  # no particles anywhere: Aabb of an empty set is zeros (util.rs:41)
             inf, sup = np.zeros(nd), np.zeros(nd)
         self.inf, self.sup, self.cutoff = inf, sup, float(self.dtype.type(cutoff))
@@ -215,7 +244,8 @@ class DistributedCellGrid:
         # top layer of this slab -> halo block (one engine kernel; also verifies slab-locality)
         n_top = self.engine.slab_top_layer(points, float(self.inf[-1]), self.cutoff, self.z_begin, self.z_end,
                                            label_offset, self._halo_send, halo_cap)
-        self._halo_send[0, 0] = float(n_top)
+        if n_top >= 0:  # engines without an on-device header write the count here
+            self._halo_send[0, 0] = float(n_top)
         ops = []
         if up < self.world:
             ops.append(dist.P2POp(dist.isend, self._halo_send, up, group=self.group))
@@ -225,6 +255,8 @@ class DistributedCellGrid:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         n_halo = int(self._halo_recv[0, 0].item()) if down >= 0 else 0
+        if n_halo > halo_cap:
+            raise ValueError(f"the neighbour's top layer exceeds halo_cap={halo_cap} rows")
         if n_local + n_halo > buf.shape[0]:
             raise ValueError(f"halo of {n_halo} rows does not fit the {buf.shape[0] - n_local} spare rows of buf")
         # persistent label array: local labels are written once, only the halo tail changes per step
@@ -261,9 +293,21 @@ class DistributedCellGrid:
         return int(self._allreduce_sum([local], self._torch.int64)[0])
 
     def lj_energy(self, cutoff: Optional[float] = None, cmp="lt", return_pairs: bool = False):
-        e, m = self.engine.lj_energy(self.cutoff if cutoff is None else cutoff, cmp, return_pairs=True)
-        # one all-reduce for both values (the pair count is exact in f64 below 2^53)
-        e_all, m_all = self._allreduce_sum([e, float(m)], self._torch.float64)
+        torch, dist = self._torch, self._dist
+        fc = self.cutoff if cutoff is None else cutoff
+        if hasattr(self.engine, "lj_energy_into") and self.backend == "nccl":
+            # device path: the kernel's results are all-reduced where they are; ONE host read.
+            # (the pair count is exact in f64 below 2^53)
+            if self._red is None:
+                self._red = torch.zeros(2, dtype=torch.float64, device=self.comm_device)
+                self._red_pairs = torch.zeros(1, dtype=torch.int64, device=self.comm_device)
+            self.engine.lj_energy_into(fc, cmp, self._red[0:1], self._red_pairs)
+            self._red[1] = self._red_pairs[0].to(torch.float64)
+            dist.all_reduce(self._red, op=dist.ReduceOp.SUM, group=self.group)
+            e_all, m_all = self._red.cpu().tolist()
+        else:
+            e, m = self.engine.lj_energy(fc, cmp, return_pairs=True)
+            e_all, m_all = self._allreduce_sum([e, float(m)], torch.float64)
         return (e_all, int(m_all)) if return_pairs else e_all
 
     def local_particle_pairs(self, cutoff: Optional[float] = None, cmp="none") -> np.ndarray:
