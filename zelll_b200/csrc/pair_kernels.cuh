@@ -45,7 +45,7 @@ namespace zb {
 #define ZB_PAIR_THREADS 256
 #endif
 #ifndef ZB_PAIR_MINBLOCKS
-#define ZB_PAIR_MINBLOCKS 4
+#define ZB_PAIR_MINBLOCKS 3
 #endif
 #ifndef ZB_PAIR_UNROLL
 #define ZB_PAIR_UNROLL 4
@@ -56,6 +56,7 @@ constexpr int kMaxNJ = 4;  // candidates held in registers per lane (register ti
 constexpr int kQueueSlots = 32 + 32 * kMaxNJ;  // per-warp hit queue: one full row + one iteration's worth
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kStageCells = 512;  // staged CSR entries per tile (cells + halo + 1)
+constexpr int kMaxTileCells = 128;  // home cells per tile (their descriptors are staged)
 
 // unsigned division by a launch-time constant (cell id -> cell coordinates) without the ~20
 // instruction integer-division sequence: q = (t + ((n - t) >> sh1)) >> sh2, t = umulhi(n, mul)
@@ -132,12 +133,15 @@ struct IntTag {
   static constexpr int value = N;
 };
 
-// candidates per lane of the exact loop.  Measured on B200 (n = 10^7 benchmark box): holding 4
-// candidates per lane raises register use to ~128 and makes the LJ consumer 2-3x slower, while
-// the count consumer does not move (the loop is instruction-issue bound either way): keep 1.
+// candidates per lane of the exact loop.  Measured on B200 (n = 10^7 benchmark box): 2 per lane
+// (one broadcast load of the home particle per 2 tests, ~78 registers, 3 CTAs/SM) is 3-5 % ahead
+// of 1; 4 per lane needs ~128 registers and is slower.
+#ifndef ZB_GENERIC_NJ
+#define ZB_GENERIC_NJ 2
+#endif
 template <class T>
 struct GenericNJ {
-  static constexpr int value = 1;
+  static constexpr int value = ZB_GENERIC_NJ;
 };
 
 // opaque copy: keeps a kernel parameter in registers instead of re-reading the constant bank
@@ -449,12 +453,16 @@ struct LjConsumer {
       if (h[k]) q[qn + __popc(b & ltmask)] = dsq[k];
       qn += __popc(b);
     }
-    while (qn >= 32) {
-      __syncwarp();
-      qn -= 32;
-      acc += (double)lj_term(q[qn + lane_id()]);
-      cnt += 1;
-      __syncwarp();
+    // at most NJ rows can have filled up
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      if (qn >= 32) {
+        __syncwarp();
+        qn -= 32;
+        acc += (double)lj_term(q[qn + lane_id()]);
+        cnt += 1;
+        __syncwarp();
+      }
     }
   }
   template <int CMP, int NJ>
@@ -513,11 +521,14 @@ struct LjConsumer {
 
 // ---------------------------------------------------------------------------------------------
 // The candidate set of home cell c: 5 runs of consecutive records (see the header comment).
-struct CellRuns {
+// The descriptor is computed ONCE per cell by one thread at tile start (cell_runs) and kept in
+// shared memory; the warp that later claims the cell reads it with three broadcast LDS.128 instead
+// of redoing ~130 instructions of index arithmetic in all 32 lanes.
+struct __align__(16) CellRuns {
   uint32_t hb, m;                 // home cell: first record, size
-  uint32_t o1, o2, o3, o4, K;     // run boundaries in candidate numbering; K = number of candidates
-  uint32_t shA, shB, shC, shD, shE;  // candidate k of run X is record k + shX
-  uint32_t first_home;            // candidates [first_home, K) are the home cell itself
+  uint32_t K, shE;                // number of candidates; candidates [K - m, K) are the home cell itself
+  uint32_t o1, o2, o3, o4;        // run boundaries in candidate numbering
+  uint32_t shA, shB, shC, shD;    // candidate k of run X is record k + shX
 
   // record of candidate k, or hb for an idle lane
   __device__ __forceinline__ uint32_t pos(uint32_t k) const {
@@ -528,6 +539,7 @@ struct CellRuns {
   // cell, the u particles before it for the home cell's u-th particle (intra-cell pairs: j
   // after i, iters.rs:29-36), none for an idle lane
   __device__ __forceinline__ uint32_t thr(uint32_t k) const {
+    const uint32_t first_home = K - m;
     return k < K ? (k >= first_home ? k - first_home : m) : 0u;
   }
 };
@@ -538,6 +550,8 @@ __device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, co
   const uint32_t hb = csrb[c], he = csrb[c + 1];
   r.hb = hb;
   r.m = he - hb;
+  r.K = r.o1 = r.o2 = r.o3 = r.o4 = 0;
+  r.shA = r.shB = r.shC = r.shD = r.shE = 0;
   if (r.m == 0) return false;
   const uint32_t w0 = (uint32_t)p.w0, w1 = (uint32_t)p.w1;
   const uint32_t row = fast_div(c, p.div0), cx = c - row * w0;
@@ -554,7 +568,6 @@ __device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, co
   const uint32_t sE = xl ? csrb[c - 1] : hb, lE = he - sE;
   r.o1 = lA; r.o2 = r.o1 + lB; r.o3 = r.o2 + lC; r.o4 = r.o3 + lD; r.K = r.o4 + lE;
   r.shA = sA; r.shB = sB - r.o1; r.shC = sC - r.o2; r.shD = sD - r.o3; r.shE = sE - r.o4;
-  r.first_home = r.K - r.m;
   return true;
 }
 
@@ -589,11 +602,9 @@ __device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uin
 }
 
 template <class T, int CMP, class Consumer>
-__device__ __forceinline__ void process_cell(const PairParams<T>& p, uint32_t c, const Rec<T>* __restrict__ recb,
-                                             const uint32_t* __restrict__ csrb, T c2, Consumer& cons) {
+__device__ __forceinline__ void process_cell(const CellRuns& r, const Rec<T>* __restrict__ recb, T c2, Consumer& cons) {
   constexpr int NJMAX = GenericNJ<T>::value;
-  CellRuns r;
-  if (!cell_runs(p, c, csrb, r)) return;
+  if (r.m == 0) return;
   const unsigned lane = lane_id();
   const Rec<T>* home = recb + r.hb;
   for (uint32_t kb = 0; kb < r.K; kb += 32 * NJMAX) {
@@ -624,6 +635,9 @@ __device__ __forceinline__ void process_cell(const PairParams<T>& p, uint32_t c,
     };
     if constexpr (NJMAX == 1) {
       run(IntTag<1>());
+    } else if constexpr (NJMAX == 2) {
+      if (nj == 1) run(IntTag<1>());
+      else run(IntTag<2>());
     } else {
       if (nj == 1) run(IntTag<1>());
       else if (nj == 2) run(IntTag<2>());
@@ -659,12 +673,9 @@ __device__ __forceinline__ void prefilter_tests(const float4* __restrict__ home,
 }
 
 template <int CMP, class Consumer>
-__device__ __forceinline__ void process_cell_prefilter(const PairParams<double>& p, uint32_t c,
-                                                       const float4* __restrict__ rel, uint32_t plo,
-                                                       const uint32_t* __restrict__ csrb, float lo, float hi,
-                                                       Consumer& cons) {
-  CellRuns r;
-  if (!cell_runs(p, c, csrb, r)) return;
+__device__ __forceinline__ void process_cell_prefilter(const CellRuns& r, const float4* __restrict__ rel, uint32_t plo,
+                                                       float lo, float hi, Consumer& cons) {
+  if (r.m == 0) return;
   const unsigned lane = lane_id();
   const float4* home = rel + (r.hb - plo);
   for (uint32_t kb = 0; kb < r.K; kb += 32 * kMaxNJ) {
@@ -704,7 +715,8 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Rec<T>* s_rec = reinterpret_cast<Rec<T>*>(smem_raw);
   float4* s_rel = reinterpret_cast<float4*>(s_rec + p.stage_recs);  // f64 + prefilter only
-  uint32_t* s_csr = reinterpret_cast<uint32_t*>(s_rel + ((kCanPrefilter && p.prefilter) ? p.stage_recs : 0u));
+  CellRuns* s_desc = reinterpret_cast<CellRuns*>(s_rel + ((kCanPrefilter && p.prefilter) ? p.stage_recs : 0u));
+  uint32_t* s_csr = reinterpret_cast<uint32_t*>(s_desc + kMaxTileCells);
   unsigned char* s_cons = reinterpret_cast<unsigned char*>(s_csr + kStageCells + 4);
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ ConsumerSmem s_cs;
@@ -756,6 +768,18 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
         bulk_g2s(s_rec, p.sorted + plo, bytes, &s_bar);
       }
       for (uint32_t k = threadIdx.x; k < ncsr; k += kPairThreads) s_csr[k] = __ldg(p.csr + cl + k);
+      __syncthreads();
+    }
+    // one thread per home cell computes the cell's run descriptor while the bulk copy is in flight
+    {
+      const uint32_t* csrb = staged ? s_csr - cl : p.csr;
+      for (uint32_t k = threadIdx.x; k < c1 - c0; k += kPairThreads) {
+        CellRuns r;
+        cell_runs(p, c0 + k, csrb, r);
+        s_desc[k] = r;
+      }
+    }
+    if (staged) {
       if (np > 0) {
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
@@ -776,14 +800,15 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
     __syncthreads();
     // warps claim home cells one at a time: the first kPairWarps statically, the rest from s_next
     for (uint32_t c = c0 + warp; c < c1;) {
+      const CellRuns r = s_desc[c - c0];
       // separate call sites so that the staged ones compile to shared-memory loads (LDS)
       if constexpr (kCanPrefilter) {
-        if (pf) process_cell_prefilter<CMP>(p, c, s_rel, plo, s_csr - cl, lo, hi, cons);
-        else if (staged) process_cell<T, CMP>(p, c, s_rec - plo, s_csr - cl, c2, cons);
-        else process_cell<T, CMP>(p, c, p.sorted, p.csr, c2, cons);
+        if (pf) process_cell_prefilter<CMP>(r, s_rel, plo, lo, hi, cons);
+        else if (staged) process_cell<T, CMP>(r, s_rec - plo, c2, cons);
+        else process_cell<T, CMP>(r, p.sorted, c2, cons);
       } else {
-        if (staged) process_cell<T, CMP>(p, c, s_rec - plo, s_csr - cl, c2, cons);
-        else process_cell<T, CMP>(p, c, p.sorted, p.csr, c2, cons);
+        if (staged) process_cell<T, CMP>(r, s_rec - plo, c2, cons);
+        else process_cell<T, CMP>(r, p.sorted, c2, cons);
       }
       uint32_t nxt = 0;
       if (lane == 0) nxt = atomicAdd(&s_next, 1u);

@@ -502,7 +502,7 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   // (opt-in: measured at parity with the exact loop on the benchmark box)
   pl.prefilter = sizeof(T) == 8 && cmp != ZB_CMP_NONE && getenv("ZB_PREFILTER") != nullptr;
   const size_t rec_bytes = sizeof(Rec<T>) + (pl.prefilter ? sizeof(float4) : 0);
-  pl.stage_recs = sizeof(T) == 8 ? (pl.prefilter ? 1280u : 1536u) : 3072u;  // 48-60 KB of stage per CTA
+  pl.stage_recs = sizeof(T) == 8 ? (pl.prefilter ? 1024u : 1408u) : 2816u;  // 44-48 KB of stage: 4 CTAs per SM
   if (const char* e = getenv("ZB_STAGE_RECS")) {     // tuning knob for experiments
     const long v = atol(e);
     if (v >= 64 && v <= 6144) pl.stage_recs = (uint32_t)v;
@@ -521,11 +521,12 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   // enough tiles to balance the persistent grid
   const uint32_t want_tiles = (uint32_t)g->sm_count * 4 * 4;
   if (nhome / std::max(tc, 1u) < want_tiles) tc = std::max<uint32_t>(8, (nhome + want_tiles - 1) / want_tiles);
-  tc = std::max<uint32_t>(tc, 1);
+  tc = std::min<uint32_t>(std::max<uint32_t>(tc, 1), kMaxTileCells);
   pl.tile_cells = tc;
   pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
   pl.blocks = (uint32_t)g->sm_count * kMaxPairCtasPerSm;  // upper bound (buffers); the launch picks the real grid
-  pl.smem = (size_t)pl.stage_recs * rec_bytes + (kStageCells + 4) * sizeof(uint32_t) + kPairWarps * warp_smem;
+  pl.smem = (size_t)pl.stage_recs * rec_bytes + kMaxTileCells * sizeof(CellRuns) + (kStageCells + 4) * sizeof(uint32_t) +
+            kPairWarps * warp_smem;
   return pl;
 }
 
