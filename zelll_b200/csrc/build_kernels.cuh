@@ -200,21 +200,32 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_kernel(const T* __restrict_
 // K2: per-particle cell id + histogram.  counts[c] += 1 with one no-return L2 atomic (RED).
 constexpr int kPointThreads = 256;
 
+// Each thread handles kPointIlp particles (block-strided so loads stay coalesced): all loads are
+// issued before the first atomic, which keeps kPointIlp L2 round trips in flight per thread.
+constexpr int kPointIlp = 1;  // measured: 4 is ~10 % slower (the kernels are bound by random sector traffic, not latency)
+
 template <class T, int NDIM>
 __global__ void __launch_bounds__(kPointThreads) count_kernel(const T* __restrict__ xyz, uint32_t n,
                                                               GridParams<T> g,
                                                               uint32_t* __restrict__ counts,
                                                               int* __restrict__ flags) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  T x, y, z;
-  load_point<T, NDIM>(xyz, i, x, y, z);
-  uint32_t c = local_cell(g, x, y, z);
-  if (c == 0xffffffffu) {
-    atomicOr(flags, 1);
-    return;
+  const uint32_t base = blockIdx.x * (kPointThreads * kPointIlp) + threadIdx.x;
+  uint32_t c[kPointIlp];
+#pragma unroll
+  for (int k = 0; k < kPointIlp; ++k) {
+    const uint32_t i = base + k * kPointThreads;
+    c[k] = 0xfffffffeu;  // beyond n
+    if (i < n) {
+      T x, y, z;
+      load_point<T, NDIM>(xyz, i, x, y, z);
+      c[k] = local_cell(g, x, y, z);
+    }
   }
-  atomicAdd(counts + c, 1u);
+#pragma unroll
+  for (int k = 0; k < kPointIlp; ++k) {
+    if (c[k] == 0xffffffffu) atomicOr(flags, 1);
+    else if (c[k] != 0xfffffffeu) atomicAdd(counts + c[k], 1u);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,14 +356,25 @@ __global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restr
                                                                 uint32_t n, GridParams<T> g,
                                                                 uint32_t* __restrict__ cursor,
                                                                 Rec<T>* __restrict__ sorted) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  T x, y, z;
-  load_point<T, NDIM>(xyz, i, x, y, z);
-  uint32_t c = local_cell(g, x, y, z);
-  if (c == 0xffffffffu) return;  // flagged by count_kernel
-  uint32_t pos = atomicAdd(cursor + c, 1u);
-  store_rec(sorted + pos, x, y, z, labels ? __ldg(labels + i) : i);
+  const uint32_t base = blockIdx.x * (kPointThreads * kPointIlp) + threadIdx.x;
+  T x[kPointIlp], y[kPointIlp], z[kPointIlp];
+  uint32_t c[kPointIlp], lab[kPointIlp], pos[kPointIlp];
+#pragma unroll
+  for (int k = 0; k < kPointIlp; ++k) {
+    const uint32_t i = base + k * kPointThreads;
+    c[k] = 0xffffffffu;
+    lab[k] = i;
+    if (i < n) {
+      load_point<T, NDIM>(xyz, i, x[k], y[k], z[k]);
+      c[k] = local_cell(g, x[k], y[k], z[k]);  // 0xffffffff: outside the window, flagged by count_kernel
+      if (labels) lab[k] = __ldg(labels + i);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kPointIlp; ++k) pos[k] = c[k] != 0xffffffffu ? atomicAdd(cursor + c[k], 1u) : 0u;
+#pragma unroll
+  for (int k = 0; k < kPointIlp; ++k)
+    if (c[k] != 0xffffffffu) store_rec(sorted + pos[k], x[k], y[k], z[k], lab[k]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -313,7 +313,7 @@ int build_sorted(zb_grid* g, const T* xyz, const uint32_t* labels, uint64_t n) {
   uint32_t* cursor = cursor_ptr(g);
   if (n > 0) {
     StageSpan span(g, ZB_STAGE_COUNT);
-    const uint32_t blocks = (uint32_t)((n + kPointThreads - 1) / kPointThreads);
+    const uint32_t blocks = (uint32_t)((n + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
     if (g->ndim == 3)
       count_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
     else
@@ -329,7 +329,7 @@ int build_sorted(zb_grid* g, const T* xyz, const uint32_t* labels, uint64_t n) {
   g->launches++;
   if (n > 0) {
     StageSpan span(g, ZB_STAGE_SCATTER);
-    const uint32_t blocks = (uint32_t)((n + kPointThreads - 1) / kPointThreads);
+    const uint32_t blocks = (uint32_t)((n + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
     Rec<T>* sorted = static_cast<Rec<T>*>(g->sorted.p);
     if (g->ndim == 3)
       scatter_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
