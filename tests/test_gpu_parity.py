@@ -394,3 +394,78 @@ def test_distributed_nccl_matches_single_gpu():
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MISMATCH" not in out.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs as parity cases
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [10_000, 100_000])
+def test_config_build_sweep(zb, n, dtype):
+    """configs[1]: CellGrid construction (benches/cellgrid.rs) f32/f64 + `<=` pair count."""
+    pts = workload.generate_points_random(n, dtype=dtype)
+    cg = zb.CellGrid(pts, 10.0, dtype=dtype)
+    og = OracleCellGrid(pts, 10.0, dtype=dtype)
+    assert np.array_equal(cg.keys(), og.keys())
+    assert cg.info().n_cells == og.info()["n_cells"]
+    assert cg.pair_count(10.0, "le") == og.pair_count(CMP_LE, 10.0)
+    assert cg.pair_count() == og.pair_count()
+
+
+def test_config_presorted_perturbed_rebuild_loop(zb):
+    """configs[3]: z-presorted cloud (examples/cachemisses.rs:57-59), repeated rebuild_mut(None) over
+    perturbed steps; every step must match the oracle's rebuild_mut of the same positions."""
+    pts = workload.presort_by_z(workload.generate_points_random(30_000))
+    cg = zb.CellGrid(pts, 10.0)
+    og = OracleCellGrid(pts, 10.0)
+    cg.track_key_changes(True)
+    cg.rebuild(pts)
+    for step in range(6):
+        pts = workload.perturb(pts, step, 0.1 * 10.0 if step % 3 else 0.0)
+        cg.rebuild_mut(pts, None)
+        changed = og.rebuild_mut(pts, None)
+        assert cg.info().keys_changed == changed
+        assert cg.pair_count(10.0, "lt") == og.pair_count(CMP_LT, 10.0)
+        e, m = cg.lj_energy(10.0, "lt", return_pairs=True)
+        _, e64, mo = og.lj_energy(CMP_LT, 10.0)
+        assert m == mo and abs(e - e64) <= F64_RTOL * abs(e64)
+
+
+def test_presorted_full_size_step_properties(zb):
+    """configs[3] at n = 10^7: the presorted cloud and its shuffled copy give the same counts and
+    (to reduction-order noise) the same energy; perturbing by 0 leaves every key unchanged."""
+    n = 10_000_000
+    pts = workload.generate_points_random(n)
+    srt = workload.presort_by_z(pts)
+    cg = zb.CellGrid(srt, 10.0)
+    e1, m1 = cg.lj_energy(10.0, "lt", return_pairs=True)
+    cg.track_key_changes(True)
+    cg.rebuild(srt)
+    cg.rebuild_mut(srt, None)
+    assert cg.info().keys_changed is False
+    cg.rebuild_mut(workload.perturb(srt, 0, 1.0), None)
+    assert cg.info().keys_changed is True
+    cg2 = zb.CellGrid(pts, 10.0)
+    e2, m2 = cg2.lj_energy(10.0, "lt", return_pairs=True)
+    assert m1 == m2 and abs(e1 - e2) <= F64_RTOL * abs(e2)
+
+
+def test_error_statuses(zb):
+    """The reference panics (cellgrid.rs:227-229, util.rs:229-232); the C ABI returns statuses."""
+    from zelll_b200 import _ffi
+
+    cg = zb.CellGrid(np.random.default_rng(0).random((100, 3)), 0.5)
+    with pytest.raises(zb.ZelllB200Error) as e:
+        cg.rebuild(np.random.default_rng(0).random((100, 3)), -1.0)
+    assert e.value.status == _ffi.ERR_BAD_ARG
+    with pytest.raises(zb.ZelllB200Error) as e:
+        cg.rebuild(np.array([[0.0, 0.0, 0.0], [1e9, 1e9, 1e9]]), 1e-3)   # 10^36 cells
+    assert e.value.status == _ffi.ERR_GRID_TOO_LARGE
+    with pytest.raises(zb.ZelllB200Error) as e:
+        cg.pair_count(1.0, "le")                                          # last rebuild failed
+    assert e.value.status == _ffi.ERR_NOT_BUILT
+    bad = np.random.default_rng(0).random((10, 3))
+    bad[3, 1] = np.inf   # (NaN follows Rust's `as i32` -> 0 and is accepted, like upstream)
+    with pytest.raises(zb.ZelllB200Error):
+        cg.rebuild(bad, 0.5)
+    cg.rebuild(np.random.default_rng(1).random((50, 3)), 0.5)            # the handle recovers
+    assert cg.info().n == 50
