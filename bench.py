@@ -197,7 +197,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import zelll_b200
-    from zelll_b200.sharded import DistributedCellGrid
+    from zelll_b200.sharded import NativeSlabGrid
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,21 +240,21 @@ def run_ours(args):
 
         engine = grid
     else:
-        spare = max(4096, int(64 * 90))  # the halo is one 3x3-cell layer (~90 particles)
+        spare = 8192  # the halo is one 3x3-cell layer (~90 particles)
         buf = slab_points(torch, rank, world, n_per, device, spare)
-        dg = DistributedCellGrid(dtype=np.float64, device=local_rank)
+        dg = NativeSlabGrid(dtype=np.float64, device=local_rank)   # NCCL driven from the C ABI
         pinned = torch.empty((n_per, 3), dtype=torch.float64).pin_memory()
         pinned.copy_(buf[:n_per])
-        engine = dg.engine
+        engine = dg
 
         def step_resident():
             dg.rebuild_slab_local(buf, n_per, CUTOFF, label_offset=rank * n_per)
-            return dg.lj_energy(CUTOFF, "lt", return_pairs=True)
+            return dg.lj_energy_allreduce(CUTOFF, "lt", return_pairs=True)
 
         def step_e2e():
             buf[:n_per].copy_(pinned, non_blocking=True)    # H2D of this rank's slab
             dg.rebuild_slab_local(buf, n_per, CUTOFF, label_offset=rank * n_per)
-            return dg.lj_energy(CUTOFF, "lt", return_pairs=True)
+            return dg.lj_energy_allreduce(CUTOFF, "lt", return_pairs=True)
 
     engine.use_stream(stream.cuda_stream)
 
@@ -304,7 +304,7 @@ def run_ours(args):
     alg_bytes = {  # ALGORITHMIC bytes per particle, f64 (SURVEY.md 8d / DESIGN.md section 4)
         "bbox": 24.0, "count": 24.0, "scan": 0.8, "scatter": 24.0 + 24.0 + 4.0, "pair_lj": 24.8,
     }
-    n_local = n_per + (getattr(dg, "n_total_local", n_per) - n_per if distributed else 0)
+    n_local = n_per + (int(dg.slab.n_halo) if distributed else 0)
     kernels = {}
     for name, (ms, cnt) in stages.items():
         if cnt and name in alg_bytes:

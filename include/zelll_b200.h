@@ -129,6 +129,35 @@ int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, 
                       int64_t z_begin, int64_t z_end, uint32_t label_offset, void* halo_rows,
                       uint64_t cap_rows, uint64_t* n_top, int* out_of_slab);
 
+/* -- native multi-GPU step (one process per GPU) ------------------------- *
+ * The same sequence zelll_b200/sharded.py drives through torch.distributed, issued by the library
+ * itself with NCCL on the handle's stream: local Aabb -> all-reduce(min/max) -> identical GridInfo
+ * on every rank -> z-layers split evenly -> top layer to rank + 1 (ncclSend/ncclRecv) -> sharded
+ * counting sort -> [pairs / LJ] -> all-reduce(sum).  No counterpart upstream (the reference's only
+ * parallelism is rayon over cells, src/cellgrid/iters.rs:282-290).  NCCL is resolved at run time
+ * (dlopen of nccl_lib_path, else the libnccl.so.2 the process already uses). */
+typedef struct zb_slab_info {
+  double inf[3], sup[3]; /* the all-reduced bounding box */
+  int32_t shape[3];
+  int32_t reserved;
+  int64_t z_begin, z_end; /* layers of the slab axis this rank owns */
+  uint64_t n_local, n_halo;
+} zb_slab_info;
+
+/* rank 0 creates the 128-byte NCCL unique id; the launcher distributes it to all ranks */
+int zb_comm_unique_id(const char* nccl_lib_path, void* out128);
+int zb_comm_init(zb_grid* g, const char* nccl_lib_path, const void* unique_id128, int world, int rank);
+
+/* Slab-local rebuild: buf (DEVICE, cap_rows x ndim values of the grid's dtype) holds this rank's
+ * n_local particles -- exactly those of its own layers -- in its first rows; the halo rows received
+ * from rank - 1 are appended behind them.  Labels are label_offset + row for local particles. */
+int zb_grid_rebuild_slab_local(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows,
+                               const double* cutoff_or_null, uint32_t label_offset, uint64_t halo_cap,
+                               zb_slab_info* out);
+
+/* zb_grid_lj_energy followed by the all-reduce(sum) of energy and pair count over the communicator */
+int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs);
+
 /* -- inspection ---------------------------------------------------------------------------- */
 
 /* CellGrid::info() (src/cellgrid.rs:346-348) */

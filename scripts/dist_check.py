@@ -14,7 +14,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import zelll_b200  # noqa: E402
 from zelll_b200 import workload  # noqa: E402
-from zelll_b200.sharded import DistributedCellGrid, slab_bounds  # noqa: E402
+from zelll_b200.sharded import DistributedCellGrid, NativeSlabGrid, slab_bounds  # noqa: E402
 
 
 def canonical(p):
@@ -37,8 +37,9 @@ def main():
     c_ref = single.pair_count(cutoff, "le")
     want = canonical(single.particle_pairs(cutoff, "lt"))
     dg = DistributedCellGrid(dtype=np.float64, device=local)
+    ng = NativeSlabGrid(dtype=np.float64, device=local)
     ok = True
-    for mode in ("general", "slab_local"):
+    for mode in ("general", "slab_local", "native"):
         if mode == "general":
             mine = np.arange(rank, n, world)
             dg.rebuild(torch.from_numpy(pts[mine]).to(dev), cutoff, labels=torch.from_numpy(mine.astype(np.int64)).to(dev))
@@ -53,11 +54,22 @@ def main():
             sel = np.nonzero((layer >= zb) & (layer < ze))[0]
             buf = torch.zeros((len(sel) + 4096, 3), dtype=torch.float64, device=dev)
             buf[: len(sel)] = torch.from_numpy(spts[sel]).to(dev)
-            dg.rebuild_slab_local(buf, len(sel), cutoff, label_offset=int(sel[0]) if len(sel) else 0)
+            off = int(sel[0]) if len(sel) else 0
+            if mode == "native":
+                ng.rebuild_slab_local(buf, len(sel), cutoff, label_offset=off)
+            else:
+                dg.rebuild_slab_local(buf, len(sel), cutoff, label_offset=off)
             to_global = order.astype(np.uint64)
-        e, m = dg.lj_energy(cutoff, "lt", return_pairs=True)
-        c = dg.pair_count(cutoff, "le")
-        local_pairs = dg.local_particle_pairs(cutoff, "lt")
+        if mode == "native":
+            e, m = ng.lj_energy_allreduce(cutoff, "lt", return_pairs=True)
+            ct = torch.tensor([ng.pair_count(cutoff, "le")], dtype=torch.int64, device=dev)
+            dist.all_reduce(ct)
+            c = int(ct.item())
+            local_pairs = ng.particle_pairs(cutoff, "lt")
+        else:
+            e, m = dg.lj_energy(cutoff, "lt", return_pairs=True)
+            c = dg.pair_count(cutoff, "le")
+            local_pairs = dg.local_particle_pairs(cutoff, "lt")
         if to_global is not None:
             local_pairs = to_global[local_pairs.astype(np.int64)]
         gathered = [None] * world

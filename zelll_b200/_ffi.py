@@ -37,6 +37,19 @@ class ZbInfo(C.Structure):
     ]
 
 
+class ZbSlabInfo(C.Structure):
+    _fields_ = [
+        ("inf", C.c_double * 3),
+        ("sup", C.c_double * 3),
+        ("shape", C.c_int32 * 3),
+        ("reserved", C.c_int32),
+        ("z_begin", C.c_int64),
+        ("z_end", C.c_int64),
+        ("n_local", C.c_uint64),
+        ("n_halo", C.c_uint64),
+    ]
+
+
 # every symbol include/zelll_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _i64, _int, _dbl = C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_double
 _dp, _u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
@@ -53,6 +66,10 @@ SIGNATURES = {
     "zb_layer_of": (_int, [_vp, _vp, _u64, _dbl, _dbl, _int, _vp]),
     "zb_slab_top_layer": (_int, [_vp, _vp, _u64, _dbl, _dbl, _i64, _i64, C.c_uint32, _vp, _u64, _u64p,
                                  C.POINTER(C.c_int)]),
+    "zb_comm_unique_id": (_int, [C.c_char_p, _vp]),
+    "zb_comm_init": (_int, [_vp, C.c_char_p, _vp, _int, _int]),
+    "zb_grid_rebuild_slab_local": (_int, [_vp, _vp, _u64, _u64, _dp, C.c_uint32, _u64, _vp]),
+    "zb_grid_lj_energy_allreduce": (_int, [_vp, _int, _dbl, _dp, _u64p]),
     "zb_grid_info": (_int, [_vp, C.POINTER(ZbInfo)]),
     "zb_grid_keys": (_int, [_vp, _vp]),
     "zb_grid_neighbor_indices": (_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -350,9 +350,21 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------
 // K4: scatter.  pos = fetch-add(table[c]) ranks the particle inside its cell; the record goes
 // out as one aligned 16 B / 32 B write.  After this kernel table[c] == end of cell c.
+// where a particle's label comes from: an explicit array, or (slab-local step) label_offset + i for
+// the first n_local particles and halo_labels[i - n_local] for the halo rows behind them
+struct LabelSrc {
+  const uint32_t* labels;
+  const uint32_t* halo_labels;
+  uint32_t offset, n_local;
+  __device__ __forceinline__ uint32_t at(uint32_t i) const {
+    if (labels) return __ldg(labels + i);
+    if (i < n_local) return offset + i;
+    return __ldg(halo_labels + (i - n_local));
+  }
+};
+
 template <class T, int NDIM>
-__global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restrict__ xyz,
-                                                                const uint32_t* __restrict__ labels,
+__global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restrict__ xyz, LabelSrc labels,
                                                                 uint32_t n, GridParams<T> g,
                                                                 uint32_t* __restrict__ cursor,
                                                                 Rec<T>* __restrict__ sorted) {
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restr
     if (i < n) {
       load_point<T, NDIM>(xyz, i, x[k], y[k], z[k]);
       c[k] = local_cell(g, x[k], y[k], z[k]);  // 0xffffffff: outside the window, flagged by count_kernel
-      if (labels) lab[k] = __ldg(labels + i);
+      lab[k] = labels.at(i);
     }
   }
 #pragma unroll
@@ -401,11 +413,39 @@ __global__ void keys_changed_kernel(const int32_t* __restrict__ old_keys, uint32
   if (o != new_keys[i]) *changed = 1;
 }
 
+// particle labels travel through f32 / f64 halo rows as raw bits
+template <class T>
+__device__ __forceinline__ T label_bits(uint32_t label);
+template <>
+__device__ __forceinline__ float label_bits<float>(uint32_t label) { return __uint_as_float(label); }
+template <>
+__device__ __forceinline__ double label_bits<double>(uint32_t label) { return __longlong_as_double((long long)label); }
+__device__ __forceinline__ uint32_t label_from_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t label_from_bits(double v) { return (uint32_t)__double_as_longlong(v); }
+
 // bbox result (T) -> 6 doubles in device memory, for all-reducing the box without a host round trip
 template <class T>
-__global__ void widen6_kernel(const T* __restrict__ in6, double* __restrict__ out6, int ndim) {
+__global__ void widen6_kernel(const T* __restrict__ in6, double* __restrict__ out6, int ndim, int negate_inf) {
   const int k = threadIdx.x;
-  if (k < 6) out6[k] = (k % 3) < ndim ? (double)in6[k] : 0.0;
+  if (k < 6) {
+    double v = (k % 3) < ndim ? (double)in6[k] : 0.0;
+    if (negate_inf && k < 3) v = -v;  // all-reduce(max) of (-inf, sup) = (-global inf, global sup)
+    out6[k] = v;
+  }
+}
+
+// received halo block -> packed coordinates behind the local particles + their labels
+template <class T, int NDIM>
+__global__ void halo_unpack_kernel(const T* __restrict__ rows, uint32_t cap, T* __restrict__ xyz_tail,
+                                   uint32_t* __restrict__ halo_labels) {
+  const uint32_t n = (uint32_t)rows[0];
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || r >= cap) return;
+  const T* row = rows + (uint64_t)(r + 1) * 4;
+  xyz_tail[(uint64_t)r * NDIM] = row[0];
+  xyz_tail[(uint64_t)r * NDIM + 1] = row[1];
+  if (NDIM == 3) xyz_tail[(uint64_t)r * NDIM + 2] = row[2];
+  halo_labels[r] = label_from_bits(row[3]);
 }
 
 // halo block header: row 0, value 0 = number of rows that follow (as a number, not as bits)
@@ -423,12 +463,6 @@ __global__ void layer_kernel(const T* __restrict__ xyz, uint32_t n, int ndim, in
   out[i] = cell_coord(__ldg(xyz + (uint64_t)i * ndim + axis), inf, cutoff);
 }
 
-template <class T>
-__device__ __forceinline__ T label_bits(uint32_t label);
-template <>
-__device__ __forceinline__ float label_bits<float>(uint32_t label) { return __uint_as_float(label); }
-template <>
-__device__ __forceinline__ double label_bits<double>(uint32_t label) { return __longlong_as_double((long long)label); }
 
 // Slab-local input check + halo extraction of the sharded host: every particle must
 // lie in layers [z_begin, z_end) of the slab axis (else *bad = 1); the particles of the TOP layer

@@ -845,6 +845,13 @@ __global__ void finalize_kernel(const double* __restrict__ block_energy,
   }
 }
 
+// (energy, pair count) -> two doubles for one all-reduce (the count is exact in f64 below 2^53)
+__global__ void pack_energy_count_kernel(const double* __restrict__ e, const unsigned long long* __restrict__ c,
+                                         double* __restrict__ out2) {
+  out2[0] = *e;
+  out2[1] = (double)*c;
+}
+
 // exclusive scan of the per-tile pair counts (a few 10^4 entries): one block, serial over chunks
 __global__ void tile_offsets_kernel(const unsigned long long* __restrict__ counts, uint32_t ntiles,
                                     unsigned long long* __restrict__ offsets) {

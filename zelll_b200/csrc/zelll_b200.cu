@@ -10,6 +10,8 @@
 #include "../../include/zelll_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -99,6 +101,25 @@ struct zb_grid {
   Misc* misc = nullptr;       // device
   Misc* h_misc = nullptr;     // pinned host mirror for small read-backs
   uint32_t pair_ntiles_cap = 0;
+
+  // native multi-GPU step (zb_comm_*): NCCL entry points resolved at run time from the NCCL the
+  // process already uses (torch's), so the library has no link-time NCCL dependency
+  struct Nccl {
+    void* dl = nullptr;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  } nccl;
+  DevBuf halo_send, halo_recv, halo_labels, red;  // halo blocks, halo labels, 8-double reduction scratch
+  double* h_red = nullptr;                        // pinned mirror of `red`
+  uint64_t n_local = 0, n_halo = 0;
 
   // optional per-stage device timing (zb_grid_profile): cudaEvent pairs around the hot launches
   bool profile = false;
@@ -280,7 +301,7 @@ int derive_shape(zb_grid* g) {
 // K2..K4 launches: counting sort of `xyz` (device) into g->sorted / g->table
 
 template <class T>
-int build_sorted(zb_grid* g, const T* xyz, const uint32_t* labels, uint64_t n) {
+int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n) {
   // window -> stored cell count
   uint64_t nc = 1;
   for (int d = 0; d < 3; ++d) {
@@ -382,7 +403,8 @@ int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
 
 template <class T>
 int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* labels_any, const double* cutoff,
-                 const double* inf, const double* sup, int64_t z_begin, int64_t z_end, bool sharded) {
+                 const double* inf, const double* sup, int64_t z_begin, int64_t z_end, bool sharded,
+                 const LabelSrc* label_src = nullptr) {
   if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
   if (n > 0 && !xyz_any) return fail(g, ZB_ERR_BAD_ARG, "xyz is NULL");
   if (cutoff) {
@@ -442,7 +464,9 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
     g->wlo[ax] = lo;
     g->wshape[ax] = std::max<int>((int)z_end - lo, 1);
   }
-  ZB_TRY(build_sorted<T>(g, xyz, labels, n));
+  LabelSrc ls{labels, nullptr, 0u, 0xffffffffu};  // no array: label = position
+  if (label_src) ls = *label_src;
+  ZB_TRY(build_sorted<T>(g, xyz, ls, n));
 
   // home-cell range of the pair kernels
   {
@@ -712,8 +736,12 @@ void zb_grid_destroy(zb_grid* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
-                    &g->block_energy, &g->block_totals, &g->out_stage};
+                    &g->block_energy, &g->block_totals, &g->out_stage, &g->halo_send, &g->halo_recv, &g->halo_labels,
+                    &g->red};
   for (DevBuf* b : bufs) free_buf(*b);
+  if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
+  if (g->nccl.dl) dlclose(g->nccl.dl);
+  if (g->h_red) cudaFreeHost(g->h_red);
   for (auto& sp : g->spans) {
     cudaEventDestroy(sp.a);
     cudaEventDestroy(sp.b);
@@ -776,8 +804,8 @@ int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6) {
   else ZB_TRY(launch_bbox<double>(g, static_cast<const double*>(dev), n));
   if (dev_out) {
     // stays on the device (asynchronous): the sharded host all-reduces it in place
-    if (g->dtype == ZB_F32) widen6_kernel<float><<<1, 32, 0, g->stream>>>(reinterpret_cast<const float*>(g->misc->out6), out6, g->ndim);
-    else widen6_kernel<double><<<1, 32, 0, g->stream>>>(reinterpret_cast<const double*>(g->misc->out6), out6, g->ndim);
+    if (g->dtype == ZB_F32) widen6_kernel<float><<<1, 32, 0, g->stream>>>(reinterpret_cast<const float*>(g->misc->out6), out6, g->ndim, 0);
+    else widen6_kernel<double><<<1, 32, 0, g->stream>>>(reinterpret_cast<const double*>(g->misc->out6), out6, g->ndim, 0);
     g->launches++;
     ZB_CUDA(cudaGetLastError());
     return ZB_OK;
@@ -1154,6 +1182,217 @@ int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cm
   if (g->dtype == ZB_F32) ZB_TRY(run(float(), true, dl));
   else ZB_TRY(run(double(), true, dl));
   if (!ldev) ZB_TRY(deliver(g, labels, dl, total * 4));
+  return ZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// native multi-GPU step: the same sequence zelll_b200/sharded.py drives through torch.distributed,
+// issued from here on the handle's stream with NCCL directly (3 host round trips per step)
+
+#define ZB_NCCL(expr)                                                                              \
+  do {                                                                                             \
+    ncclResult_t r__ = (expr);                                                                     \
+    if (r__ != ncclSuccess)                                                                        \
+      return fail(g, ZB_ERR_CUDA, "%s failed: %s", #expr,                                          \
+                  g->nccl.GetErrorString ? g->nccl.GetErrorString(r__) : "nccl error");            \
+  } while (0)
+
+}  // extern "C"
+
+static int nccl_load(zb_grid* g, const char* path) {
+  if (g->nccl.dl) return ZB_OK;
+  const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+  void* dl = nullptr;
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    dl = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (dl) break;
+  }
+  if (!dl) return fail(g, ZB_ERR_CUDA, "cannot load NCCL: %s", dlerror());
+  auto sym = [&](const char* n) { return dlsym(dl, n); };
+  auto& N = g->nccl;
+  N.dl = dl;
+  N.CommInitRank = reinterpret_cast<decltype(N.CommInitRank)>(sym("ncclCommInitRank"));
+  N.CommDestroy = reinterpret_cast<decltype(N.CommDestroy)>(sym("ncclCommDestroy"));
+  N.AllReduce = reinterpret_cast<decltype(N.AllReduce)>(sym("ncclAllReduce"));
+  N.Send = reinterpret_cast<decltype(N.Send)>(sym("ncclSend"));
+  N.Recv = reinterpret_cast<decltype(N.Recv)>(sym("ncclRecv"));
+  N.GroupStart = reinterpret_cast<decltype(N.GroupStart)>(sym("ncclGroupStart"));
+  N.GroupEnd = reinterpret_cast<decltype(N.GroupEnd)>(sym("ncclGroupEnd"));
+  N.GetErrorString = reinterpret_cast<decltype(N.GetErrorString)>(sym("ncclGetErrorString"));
+  if (!N.CommInitRank || !N.AllReduce || !N.Send || !N.Recv || !N.GroupStart || !N.GroupEnd)
+    return fail(g, ZB_ERR_CUDA, "NCCL library lacks a required symbol");
+  return ZB_OK;
+}
+
+extern "C" {
+
+int zb_comm_unique_id(const char* nccl_lib_path, void* out128) {
+  if (!out128) return ZB_ERR_BAD_ARG;
+  const char* cands[] = {nccl_lib_path, "libnccl.so.2", "libnccl.so"};
+  void* dl = nullptr;
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    dl = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (dl) break;
+  }
+  if (!dl) return ZB_ERR_CUDA;
+  auto get = reinterpret_cast<ncclResult_t (*)(ncclUniqueId*)>(dlsym(dl, "ncclGetUniqueId"));
+  if (!get) return ZB_ERR_CUDA;
+  ncclUniqueId id;
+  if (get(&id) != ncclSuccess) return ZB_ERR_CUDA;
+  memcpy(out128, &id, sizeof id);
+  return ZB_OK;
+}
+
+int zb_comm_init(zb_grid* g, const char* nccl_lib_path, const void* unique_id128, int world, int rank) {
+  ZB_TRY(enter(g));
+  if (!unique_id128 || world < 1 || rank < 0 || rank >= world) return fail(g, ZB_ERR_BAD_ARG, "bad communicator arguments");
+  ZB_TRY(nccl_load(g, nccl_lib_path));
+  if (g->nccl.comm) {
+    g->nccl.CommDestroy(g->nccl.comm);
+    g->nccl.comm = nullptr;
+  }
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, sizeof id);
+  ZB_NCCL(g->nccl.CommInitRank(&g->nccl.comm, world, id, rank));
+  g->nccl.world = world;
+  g->nccl.rank = rank;
+  ZB_TRY(reserve(g, g->red, 8 * sizeof(double)));
+  if (!g->h_red) ZB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g->h_red), 8 * sizeof(double)));
+  return ZB_OK;
+}
+
+}  // extern "C"
+
+template <class T>
+static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows, const double* cutoff,
+                          uint32_t label_offset, uint64_t halo_cap, zb_slab_info* out) {
+  auto& N = g->nccl;
+  if (!N.comm) return fail(g, ZB_ERR_NOT_BUILT, "zb_comm_init has not been called");
+  if (n_local > 2147483647ull || cap_rows < n_local) return fail(g, ZB_ERR_BAD_ARG, "bad n_local / cap_rows");
+  if (!buf || !is_device_ptr(buf)) return fail(g, ZB_ERR_BAD_ARG, "buf must be device memory");
+  if (cutoff) {
+    const T c = (T)*cutoff;
+    if (!(c > (T)0) || !std::isfinite((double)c)) return fail(g, ZB_ERR_BAD_ARG, "cutoff must be positive and finite");
+    g->cutoff = (double)c;
+  }
+  g->built = false;
+  T* xyz = static_cast<T*>(buf);
+  double* red = static_cast<double*>(g->red.p);
+  const int nd = g->ndim;
+
+  // 1. global box: local K1 -> (-inf, sup) -> all-reduce(max) -> host
+  if (n_local) {
+    ZB_TRY(launch_bbox<T>(g, xyz, n_local));
+    widen6_kernel<T><<<1, 32, 0, g->stream>>>(reinterpret_cast<const T*>(g->misc->out6), red, nd, 1);
+    g->launches++;
+  } else {
+    const double empty[6] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    ZB_CUDA(cudaMemcpyAsync(red, empty, sizeof empty, cudaMemcpyHostToDevice, g->stream));
+  }
+  ZB_NCCL(N.AllReduce(red, red, 6, ncclDouble, ncclMax, N.comm, g->stream));
+  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 6 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  double inf[3] = {0, 0, 0}, sup[3] = {0, 0, 0};
+  bool any = true;
+  for (int d = 0; d < nd; ++d) {
+    inf[d] = -g->h_red[d];
+    sup[d] = g->h_red[3 + d];
+    any = any && std::isfinite(inf[d]) && std::isfinite(sup[d]);
+  }
+  if (!any)  // no particle anywhere: Aabb of an empty set is zeros (util.rs:41)
+    for (int d = 0; d < 3; ++d) inf[d] = sup[d] = 0.0;
+  for (int d = 0; d < 3; ++d) {
+    g->inf[d] = inf[d];
+    g->sup[d] = sup[d];
+  }
+  ZB_TRY(derive_shape<T>(g));
+  const int ax = nd - 1;
+  const int64_t nz = g->shape[ax];
+  const int64_t z_begin = (int64_t)N.rank * nz / N.world, z_end = (int64_t)(N.rank + 1) * nz / N.world;
+
+  // 2. halo: top layer of this slab -> rank + 1, top layer of rank - 1 -> behind the local rows
+  const size_t block = (halo_cap + 1) * 4 * sizeof(T);
+  ZB_TRY(reserve(g, g->halo_send, block));
+  ZB_TRY(reserve(g, g->halo_recv, block));
+  ZB_TRY(reserve(g, g->halo_labels, std::max<uint64_t>(halo_cap, 1) * 4));
+  ZB_TRY(zb_slab_top_layer(g, xyz, n_local, inf[ax], g->cutoff, z_begin, z_end, label_offset, g->halo_send.p, halo_cap,
+                           nullptr, nullptr));
+  const bool up = N.rank + 1 < N.world, down = N.rank > 0;
+  uint64_t n_halo = 0;
+  if (up || down) {
+    ZB_NCCL(N.GroupStart());
+    if (up) ZB_NCCL(N.Send(g->halo_send.p, block, ncclChar, N.rank + 1, N.comm, g->stream));
+    if (down) ZB_NCCL(N.Recv(g->halo_recv.p, block, ncclChar, N.rank - 1, N.comm, g->stream));
+    ZB_NCCL(N.GroupEnd());
+  }
+  if (down) {
+    ZB_CUDA(cudaMemcpyAsync(g->h_red, g->halo_recv.p, sizeof(T), cudaMemcpyDeviceToHost, g->stream));
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    n_halo = (uint64_t) * reinterpret_cast<const T*>(g->h_red);
+    if (n_halo > halo_cap) return fail(g, ZB_ERR_CAPACITY, "the neighbour's top layer exceeds halo_cap = %llu rows", (unsigned long long)halo_cap);
+    if (n_local + n_halo > cap_rows) return fail(g, ZB_ERR_CAPACITY, "buf has no room for %llu halo rows", (unsigned long long)n_halo);
+    if (n_halo) {
+      const uint32_t blocks = (uint32_t)((n_halo + 255) / 256);
+      if (nd == 3)
+        halo_unpack_kernel<T, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)halo_cap,
+                                                                xyz + n_local * 3, static_cast<uint32_t*>(g->halo_labels.p));
+      else
+        halo_unpack_kernel<T, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)halo_cap,
+                                                                xyz + n_local * 2, static_cast<uint32_t*>(g->halo_labels.p));
+      g->launches++;
+      ZB_CUDA(cudaGetLastError());
+    }
+  }
+
+  // 3. sharded rebuild with the imposed box (K2-K4); labels come from (offset + i | halo labels)
+  LabelSrc ls{nullptr, static_cast<const uint32_t*>(g->halo_labels.p), label_offset, (uint32_t)n_local};
+  ZB_TRY(rebuild_impl<T>(g, xyz, n_local + n_halo, nullptr, nullptr, inf, sup, z_begin, z_end, true, &ls));
+  g->n_local = n_local;
+  g->n_halo = n_halo;
+  if (out) {
+    memset(out, 0, sizeof *out);
+    for (int d = 0; d < 3; ++d) {
+      out->inf[d] = g->inf[d];
+      out->sup[d] = g->sup[d];
+      out->shape[d] = d < nd ? g->shape[d] : 0;
+    }
+    out->z_begin = z_begin;
+    out->z_end = z_end;
+    out->n_local = n_local;
+    out->n_halo = n_halo;
+  }
+  return ZB_OK;
+}
+
+extern "C" {
+
+int zb_grid_rebuild_slab_local(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows, const double* cutoff_or_null,
+                               uint32_t label_offset, uint64_t halo_cap, zb_slab_info* out) {
+  ZB_TRY(enter(g));
+  return g->dtype == ZB_F32 ? slab_step_impl<float>(g, buf, n_local, cap_rows, cutoff_or_null, label_offset, halo_cap, out)
+                            : slab_step_impl<double>(g, buf, n_local, cap_rows, cutoff_or_null, label_offset, halo_cap, out);
+}
+
+int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs) {
+  ZB_TRY(enter(g));
+  ZB_TRY(check_built(g));
+  auto& N = g->nccl;
+  if (!N.comm) return fail(g, ZB_ERR_NOT_BUILT, "zb_comm_init has not been called");
+  if (!energy) return fail(g, ZB_ERR_BAD_ARG, "energy is NULL");
+  if (cmp < 1 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "lj energy needs a distance filter (cmp LT or LE)");
+  if (g->dtype == ZB_F32) ZB_TRY(lj_impl<float>(g, cmp, filter_cutoff));
+  else ZB_TRY(lj_impl<double>(g, cmp, filter_cutoff));
+  // (energy, pair count as f64: exact below 2^53) -> one all-reduce(sum) -> host
+  double* red = static_cast<double*>(g->red.p);
+  pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, red);
+  g->launches++;
+  ZB_NCCL(N.AllReduce(red, red, 2, ncclDouble, ncclSum, N.comm, g->stream));
+  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 2 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  *energy = g->h_red[0];
+  if (n_pairs) *n_pairs = (uint64_t)g->h_red[1];
   return ZB_OK;
 }
 

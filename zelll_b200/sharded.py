@@ -125,6 +125,69 @@ class ShardedCellGrid(CellGrid):
             self._cutoff = float(self.dtype.type(cutoff))
 
 
+def nccl_library_path() -> str:
+    """The NCCL shared library this process already uses (torch's bundled one), for zb_comm_init."""
+    import glob
+    import os
+
+    import torch
+
+    site = os.path.dirname(os.path.dirname(torch.__file__))
+    for pat in (os.path.join(site, "nvidia", "nccl", "lib", "libnccl.so*"),
+                os.path.join(os.path.dirname(torch.__file__), "lib", "libnccl.so*")):
+        hits = sorted(glob.glob(pat))
+        if hits:
+            return hits[0]
+    return "libnccl.so.2"
+
+
+class NativeSlabGrid(ShardedCellGrid):
+    """Slab-local multi-GPU step driven by the library itself (zb_comm_init, zb_grid_rebuild_slab_local,
+    zb_grid_lj_energy_allreduce): NCCL is called from C on the handle's stream, three host round trips
+    per step.  torch.distributed is used once, to hand rank 0's NCCL unique id to the other ranks."""
+
+    def __init__(self, *, dtype=np.float64, ndim: int = 3, device: int = 0, group=None):
+        import torch.distributed as dist
+
+        super().__init__(dtype=dtype, ndim=ndim, device=device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        path = nccl_library_path().encode()
+        uid = C.create_string_buffer(128)
+        if self.rank == 0:
+            rc = self._lib.zb_comm_unique_id(path, uid)
+            if rc != _ffi.OK:
+                raise _ffi.ZelllB200Error(rc, "ncclGetUniqueId failed")
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = C.create_string_buffer(box[0], 128)
+        self._check(self._lib.zb_comm_init(self._h, path, uid, self.world, self.rank))
+        self.slab = None
+
+    def rebuild_slab_local(self, buf, n_local: int, cutoff: Optional[float], label_offset: int, halo_cap: int = 8192):
+        """buf: CUDA tensor [cap_rows, ndim]; rows [0, n_local) are this rank's own layers, the halo is
+        appended behind them.  Returns the zb_slab_info of the step."""
+        if not (_is_torch(buf) and buf.is_cuda):
+            raise ValueError("buf must be a CUDA tensor")
+        import torch
+
+        self.use_stream(torch.cuda.current_stream(buf.device).cuda_stream)
+        info = _ffi.ZbSlabInfo()
+        self._check(self._lib.zb_grid_rebuild_slab_local(self._h, buf.data_ptr(), int(n_local), int(buf.shape[0]),
+                                                         self._optional(cutoff), int(label_offset) & 0xFFFFFFFF,
+                                                         int(halo_cap), C.byref(info)))
+        self._points, self._label_map = buf, None
+        if cutoff is not None:
+            self._cutoff = float(self.dtype.type(cutoff))
+        self.slab = info
+        return info
+
+    def lj_energy_allreduce(self, cutoff: Optional[float] = None, cmp="lt", return_pairs: bool = False):
+        code, fc = self._filter(cutoff, cmp)
+        e, m = C.c_double(0.0), C.c_uint64(0)
+        self._check(self._lib.zb_grid_lj_energy_allreduce(self._h, code, fc, C.byref(e), C.byref(m)))
+        return (e.value, int(m.value)) if return_pairs else e.value
+
+
 class DistributedCellGrid:
     """torch.distributed orchestration of one ShardedCellGrid per rank."""
 
