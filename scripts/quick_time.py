@@ -15,6 +15,7 @@ def main():
     for name, fn in [("rebuild", lambda: cg.rebuild(t)), ("pair_count_le", lambda: cg.pair_count(10.0, "le")),
                      ("pair_count_none", lambda: cg.pair_count()),
                      ("lj_energy", lambda: cg.lj_energy(10.0, "lt")),
+                     ("pairs_device_lt", lambda: cg.particle_pairs_device(10.0, "lt", capacity=170_000_000 * n // 10_000_000).shape),
                      ("rebuild+lj", lambda: (cg.rebuild(t), cg.lj_energy(10.0, "lt")))]:
         for _ in range(3): fn()
         torch.cuda.synchronize()

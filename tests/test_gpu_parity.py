@@ -469,3 +469,13 @@ def test_error_statuses(zb):
         cg.rebuild(bad, 0.5)
     cg.rebuild(np.random.default_rng(1).random((50, 3)), 0.5)            # the handle recovers
     assert cg.info().n == 50
+
+
+def test_very_sparse_box(zb):
+    """zelll's home turf: few particles in a huge box (10^8 cells here, almost all empty).  The dense
+    cell table still gives the reference's pair set; empty tiles are skipped."""
+    rng = np.random.default_rng(7)
+    blobs = np.array([[0.0, 0.0, 0.0], [450.0, 20.0, 460.0], [30.0, 440.0, 10.0]])
+    pts = blobs[rng.integers(0, 3, 6000)] + rng.normal(0.0, 1.5, (6000, 3))
+    cg, og = _check_against_oracle(zb, pts, 1.0, np.float64, 3)
+    assert int(np.prod(cg.info().shape().astype(np.int64))) > 5e7

@@ -339,6 +339,24 @@ class CellGrid:
             self._check(self._lib.zb_grid_pairs(self._h, code, fc, out.ctypes.data, m, C.byref(n_out)))
         return self._map_labels(out)
 
+    def particle_pairs_device(self, cutoff: Optional[float] = None, cmp="none", capacity: Optional[int] = None):
+        """`particle_pairs()` materialised in HBM: a torch CUDA tensor (m, 2) int32 (the bits are uint32
+        labels).  `capacity` (rows) skips the sizing call when the caller knows an upper bound."""
+        import torch
+
+        code, fc = self._filter(cutoff, cmp)
+        n_out = C.c_uint64(0)
+        dev = torch.device("cuda", self.device)
+        self.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+        if capacity is None:
+            rc = self._lib.zb_grid_pairs(self._h, code, fc, None, 0, C.byref(n_out))
+            if rc not in (_ffi.OK, _ffi.ERR_CAPACITY):
+                self._check(rc)
+            capacity = int(n_out.value)
+        out = torch.empty((max(int(capacity), 1), 2), dtype=torch.int32, device=dev)
+        self._check(self._lib.zb_grid_pairs(self._h, code, fc, out.data_ptr(), int(capacity), C.byref(n_out)))
+        return out[: int(n_out.value)]
+
     def par_particle_pairs(self, cutoff: Optional[float] = None, cmp="none", chunks: int = 16):
         """`par_particle_pairs()` (cellgrid.rs:447-451): the enumeration itself is parallel on the
         device; callers get the materialised list split into `chunks` slices to fan out over."""

@@ -82,6 +82,8 @@ struct PairParams {
   T cell;               // edge length of a grid cell (the grid's cutoff)
   int prefilter;        // f64 only: run staged tiles through the f32 prefilter
   FastDiv div0, div1;   // division by w0 and by w1
+  const uint32_t* tile_list;   // sparse boxes: ids of the tiles that hold home particles, else nullptr
+  const uint32_t* tile_list_n; // ... and their number (device memory)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -733,13 +735,17 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
 
   const uint32_t plane = (uint32_t)p.w0 * (uint32_t)p.w1;
   const uint32_t halo = plane + (uint32_t)p.w0 + 1u;
-  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  const uint32_t nwork = p.tile_list ? __ldg(p.tile_list_n) : p.ntiles;
+  for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const uint32_t tile = p.tile_list ? __ldg(p.tile_list + w) : w;
     const uint32_t c0 = p.home_lo + tile * p.tile_cells;
     const uint32_t c1 = min(c0 + p.tile_cells, p.home_hi);
     const uint32_t cl = c0 > halo ? c0 - halo : 0u;
     const uint32_t ncsr = c1 - cl + 1;
     const uint32_t plo = __ldg(p.csr + cl), phi = __ldg(p.csr + c1);
     const uint32_t np = phi - plo;
+    // sparse boxes: a tile without home particles has no pairs (its per-tile count stays 0)
+    if (phi == __ldg(p.csr + c0)) continue;
     const bool staged = np <= p.stage_recs && ncsr <= (uint32_t)kStageCells;
 
     // prefilter thresholds of this tile (warp-uniform)
@@ -759,7 +765,7 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
       }
     }
 
-    cons.tile_begin(tile, s_rec, pf);
+    cons.tile_begin(w, s_rec, pf);  // per-tile arrays are indexed by work item (= tile id unless sparse)
     if (threadIdx.x == 0) s_next = c0 + kPairWarps;
     if (staged) {
       if (threadIdx.x == 0 && np > 0) {
@@ -814,7 +820,7 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
       if (lane == 0) nxt = atomicAdd(&s_next, 1u);
       c = __shfl_sync(0xffffffffu, nxt, 0);
     }
-    cons.template tile_end<CMP>(tile);  // ends with __syncthreads(): the stage buffers may be overwritten
+    cons.template tile_end<CMP>(w);  // ends with __syncthreads(): the stage buffers may be overwritten
   }
   cons.finish();
 }
@@ -845,6 +851,25 @@ __global__ void finalize_kernel(const double* __restrict__ block_energy,
   }
 }
 
+// sparse boxes: the tiles whose home cells hold at least one particle (order unspecified)
+__global__ void tile_list_kernel(const uint32_t* __restrict__ csr, uint32_t home_lo, uint32_t home_hi,
+                                 uint32_t tile_cells, uint32_t ntiles, uint32_t* __restrict__ list,
+                                 uint32_t* __restrict__ count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  if (t < ntiles) {
+    const uint32_t c0 = home_lo + t * tile_cells;
+    const uint32_t c1 = min(c0 + tile_cells, home_hi);
+    live = __ldg(csr + c1) != __ldg(csr + c0);
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, live);
+  if (b == 0) return;
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(count, (uint32_t)__popc(b));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (live) list[base + __popc(b & lanemask_lt())] = t;
+}
+
 // (energy, pair count) -> two doubles for one all-reduce (the count is exact in f64 below 2^53)
 __global__ void pack_energy_count_kernel(const double* __restrict__ e, const unsigned long long* __restrict__ c,
                                          double* __restrict__ out2) {
@@ -854,9 +879,10 @@ __global__ void pack_energy_count_kernel(const double* __restrict__ e, const uns
 
 // exclusive scan of the per-tile pair counts (a few 10^4 entries): one block, serial over chunks
 __global__ void tile_offsets_kernel(const unsigned long long* __restrict__ counts, uint32_t ntiles,
-                                    unsigned long long* __restrict__ offsets) {
+                                    const uint32_t* __restrict__ ntiles_dev, unsigned long long* __restrict__ offsets) {
   __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
+  if (ntiles_dev) ntiles = *ntiles_dev;  // sparse boxes: number of listed tiles
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -60,6 +60,12 @@ struct Misc {
 
 }  // namespace
 
+struct PairPlan {
+  uint32_t tile_cells, ntiles, stage_recs, blocks;
+  size_t smem;
+  bool prefilter;
+};
+
 struct zb_grid {
   int device = 0;
   int dtype = ZB_F64;
@@ -98,6 +104,9 @@ struct zb_grid {
   DevBuf keys_old, keys_new;
   DevBuf tile_counts, tile_offsets, block_energy, block_totals;
   DevBuf out_stage; // staging for host-destination outputs
+  DevBuf tile_list; // sparse boxes: [count, tile ids...] of the tiles with home particles
+  uint64_t tile_list_build = ~0ull;  // build_id / tile_cells the list was made for
+  uint32_t tile_list_cells = 0;
   Misc* misc = nullptr;       // device
   Misc* h_misc = nullptr;     // pinned host mirror for small read-backs
   uint32_t pair_ntiles_cap = 0;
@@ -120,6 +129,13 @@ struct zb_grid {
   DevBuf halo_send, halo_recv, halo_labels, red;  // halo blocks, halo labels, 8-double reduction scratch
   double* h_red = nullptr;                        // pinned mirror of `red`
   uint64_t n_local = 0, n_halo = 0;
+  uint64_t build_id = 0;  // bumped by every rebuild
+  // zb_grid_pairs: per-tile counts of the last sizing pass (still in tile_counts)
+  bool emit_cache_valid = false;
+  uint64_t emit_cache_build = 0, emit_cache_total = 0;
+  int emit_cache_cmp = 0;
+  double emit_cache_fc = 0.0;
+  PairPlan emit_cache_plan{};
 
   // optional per-stage device timing (zb_grid_profile): cudaEvent pairs around the hot launches
   bool profile = false;
@@ -413,6 +429,8 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
     g->cutoff = (double)c;
   }
   g->built = false;
+  g->build_id++;
+  g->emit_cache_valid = false;
   const void* dev = nullptr;
   ZB_TRY(stage_input(g, xyz_any, n, &dev));
   const T* xyz = static_cast<const T*>(dev);
@@ -513,12 +531,6 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
 // ---------------------------------------------------------------------------------------------
 // pair kernels
 
-struct PairPlan {
-  uint32_t tile_cells, ntiles, stage_recs, blocks;
-  size_t smem;
-  bool prefilter;
-};
-
 template <class T>
 PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   PairPlan pl;
@@ -583,13 +595,38 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.fc = c;
   p.cell = (T)g->cutoff;
   p.prefilter = pl.prefilter ? 1 : 0;
+  p.tile_list = nullptr;
+  p.tile_list_n = nullptr;
   p.div0 = make_fastdiv((uint32_t)g->wshape[0]);
   p.div1 = make_fastdiv((uint32_t)g->wshape[1]);
   return p;
 }
 
+// Sparse boxes (few of the stored cells hold particles): list the tiles that have home particles
+// once per build so the persistent CTAs do not walk millions of empty tiles.
+template <class T>
+int sparse_tile_list(zb_grid* g, const PairPlan& pl, PairParams<T>& p) {
+  if (pl.ntiles < 4096 || g->n_cells_nonempty * 8 > (uint64_t)g->ncells) return ZB_OK;  // dense enough
+  ZB_TRY(reserve(g, g->tile_list, ((size_t)pl.ntiles + 1) * 4));
+  uint32_t* buf = static_cast<uint32_t*>(g->tile_list.p);
+  if (g->tile_list_build != g->build_id || g->tile_list_cells != pl.tile_cells) {
+    ZB_CUDA(cudaMemsetAsync(buf, 0, 4, g->stream));
+    tile_list_kernel<<<(pl.ntiles + 255) / 256, 256, 0, g->stream>>>(csr_ptr(g), g->home_lo, g->home_hi, pl.tile_cells,
+                                                                 pl.ntiles, buf + 1, buf);
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    g->tile_list_build = g->build_id;
+    g->tile_list_cells = pl.tile_cells;
+  }
+  p.tile_list = buf + 1;
+  p.tile_list_n = buf;
+  return ZB_OK;
+}
+
 template <class T, class Consumer>
-int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p, typename Consumer::Args args) {
+int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, typename Consumer::Args args) {
+  PairParams<T> p = p_in;
+  ZB_TRY(sparse_tile_list<T>(g, pl, p));
   auto go = [&](auto kern) -> int {
     ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     // persistent grid: one wave of resident CTAs
@@ -635,6 +672,7 @@ int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* pla
   a.tile_counts = per_tile ? static_cast<unsigned long long*>(g->tile_counts.p) : nullptr;
   a.block_totals = static_cast<unsigned long long*>(g->block_totals.p);
   ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
+  if (per_tile) ZB_CUDA(cudaMemsetAsync(g->tile_counts.p, 0, ((size_t)pl.ntiles + 1) * 8, g->stream));
   if (pl.ntiles) ZB_TRY((launch_pairs<T, CountConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
   ZB_TRY(finalize(g, false, pl.blocks));
   if (plan_out) *plan_out = pl;
@@ -658,7 +696,11 @@ int lj_impl(zb_grid* g, int cmp, double fc) {
 
 template <class T>
 int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev) {
+  // per-tile arrays are indexed by work item: all tiles, or (sparse boxes) the listed ones
+  const bool sparse = g->tile_list_build == g->build_id && g->tile_list_cells == pl.tile_cells && g->tile_list.p &&
+                      !(pl.ntiles < 4096 || g->n_cells_nonempty * 8 > (uint64_t)g->ncells);
   tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), pl.ntiles,
+                                                 sparse ? static_cast<const uint32_t*>(g->tile_list.p) : nullptr,
                                                  static_cast<unsigned long long*>(g->tile_offsets.p));
   g->launches++;
   typename EmitConsumer<T>::Args a;
@@ -736,7 +778,7 @@ void zb_grid_destroy(zb_grid* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
-                    &g->block_energy, &g->block_totals, &g->out_stage, &g->halo_send, &g->halo_recv, &g->halo_labels,
+                    &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->halo_send, &g->halo_recv, &g->halo_labels,
                     &g->red};
   for (DevBuf* b : bufs) free_buf(*b);
   if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
@@ -1065,12 +1107,28 @@ int zb_grid_pairs(zb_grid* g, int cmp, double filter_cutoff, uint32_t* ij, uint6
   ZB_TRY(check_built(g));
   if (!n_out) return fail(g, ZB_ERR_BAD_ARG, "n_out is NULL");
   if (cmp < 0 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+  // pass 1 (per-tile counts) is reused when the caller sizes first and then fetches: same grid
+  // build, same filter -> the cached tile counts are still exact
   PairPlan pl;
-  if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff, true, &pl));
-  else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff, true, &pl));
-  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->pair_total, &g->misc->pair_total, 8, cudaMemcpyDeviceToHost, g->stream));
-  ZB_CUDA(cudaStreamSynchronize(g->stream));
-  const uint64_t total = g->h_misc->pair_total;
+  uint64_t total;
+  if (g->emit_cache_valid && g->emit_cache_build == g->build_id && g->emit_cache_cmp == cmp &&
+      g->emit_cache_fc == filter_cutoff) {
+    pl = g->emit_cache_plan;
+    total = g->emit_cache_total;
+  } else {
+    g->emit_cache_valid = false;
+    if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff, true, &pl));
+    else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff, true, &pl));
+    ZB_CUDA(cudaMemcpyAsync(&g->h_misc->pair_total, &g->misc->pair_total, 8, cudaMemcpyDeviceToHost, g->stream));
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    total = g->h_misc->pair_total;
+    g->emit_cache_plan = pl;
+    g->emit_cache_total = total;
+    g->emit_cache_build = g->build_id;
+    g->emit_cache_cmp = cmp;
+    g->emit_cache_fc = filter_cutoff;
+    g->emit_cache_valid = true;
+  }
   *n_out = total;
   if (total > cap || (total && !ij))
     return fail(g, ZB_ERR_CAPACITY, "pair list needs %llu rows, capacity is %llu", (unsigned long long)total,
@@ -1157,10 +1215,11 @@ int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cm
   // pass 1: counts -> exclusive scan -> offsets
   if (g->dtype == ZB_F32) ZB_TRY(run(float(), false, nullptr));
   else ZB_TRY(run(double(), false, nullptr));
+  g->emit_cache_valid = false;  // tile_counts is reused below
   ZB_TRY(reserve(g, g->tile_counts, (nq + 1) * 8));
   ZB_CUDA(cudaMemcpyAsync(g->tile_counts.p, doff, nq * 8, cudaMemcpyDeviceToDevice, g->stream));
   tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), (uint32_t)nq,
-                                                 doff);
+                                                 nullptr, doff);
   g->launches++;
   ZB_CUDA(cudaGetLastError());
   ZB_CUDA(cudaMemcpyAsync(&g->h_misc->pair_total, doff + nq, 8, cudaMemcpyDeviceToHost, g->stream));
