@@ -243,8 +243,10 @@ def run_ours(args):
         spare = 8192  # the halo is one 3x3-cell layer (~90 particles)
         buf = slab_points(torch, rank, world, n_per, device, spare)
         dg = NativeSlabGrid(dtype=np.float64, device=local_rank)   # NCCL driven from the C ABI
-        pinned = torch.empty((n_per, 3), dtype=torch.float64).pin_memory()
-        pinned.copy_(buf[:n_per])
+        pinned = None
+        if not args.no_e2e:
+            pinned = torch.empty((n_per, 3), dtype=torch.float64).pin_memory()
+            pinned.copy_(buf[:n_per])
         engine = dg
 
         def step_resident():
@@ -288,9 +290,12 @@ def run_ours(args):
         energy, pairs = step_resident()
     ms_total, (energy, pairs), launches, stages = timed(step_resident, steps, profile=True)
     # ---- the same step end to end from pinned host memory --------------------------------------
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, (energy_e, pairs_e), _, _ = timed(step_e2e, steps)
+    if args.no_e2e:
+        ms_e2e, pairs_e = float("nan"), 0
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, (energy_e, pairs_e), _, _ = timed(step_e2e, steps)
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / steps
@@ -339,8 +344,9 @@ def run_ours(args):
         "metric": METRIC, "value": total_pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": _config(world, n_per),
-        "e2e": {"value": int(pairs_e) / (ms_step_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_step_e2e,
-                "h2d_bytes_per_step": n_per * 24 * world, "d2h_bytes_per_step": 16 * world},
+        "e2e": None if args.no_e2e else {"value": int(pairs_e) / (ms_step_e2e * 1e-3), "unit": UNIT,
+                                         "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": n_per * 24 * world,
+                                         "d2h_bytes_per_step": 16 * world},
         "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "clocks": clocks, "pairs_per_step": total_pairs, "energy": energy,
         "particles_per_s": n_per * world / (ms_step * 1e-3),
@@ -358,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (very large --n-per-gpu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
