@@ -479,3 +479,33 @@ def test_very_sparse_box(zb):
     pts = blobs[rng.integers(0, 3, 6000)] + rng.normal(0.0, 1.5, (6000, 3))
     cg, og = _check_against_oracle(zb, pts, 1.0, np.float64, 3)
     assert int(np.prod(cg.info().shape().astype(np.int64))) > 5e7
+
+
+def test_gridcell_views_reference_counts(zb, golden):
+    """GridCell-level API (iters.rs:121-290) on the reference's own fixtures: 14 non-empty cells
+    (iters.rs:299-308), sum of cell sizes = n (:311-331), 4 intra + 24 inter half-space pairs on the
+    2x2x2 chessboard (:334-356), Full = 2 x Half (:359-387)."""
+    g = golden["test_cellgrid_iter"]
+    pts = oracle.generate_pointcloud(g["shape"], g["cutoff"], g["origin"])
+    cg = zb.CellGrid(pts, g["cutoff"])
+    cells = cg.iter_cells()
+    assert len(cells) == g["nonempty_cells"]
+    assert sum(len(c) for c in cells) == len(pts)
+    assert sum(len(ch) for ch in cg.par_iter_cells(4)) == len(cells)
+    g2 = golden["test_neighborcell_particle_pairs"]
+    pts2 = oracle.generate_pointcloud(g2["shape"], g2["cutoff"], g2["origin"])
+    cg2 = zb.CellGrid(pts2, g2["cutoff"])
+    intra = sum(len(c.intra_cell_pairs()) for c in cg2.iter_cells())
+    inter = sum(len(c.inter_cell_pairs()) for c in cg2.iter_cells())
+    assert (intra, inter) == (g2["intra_half"], g2["inter_half"])
+    g3 = golden["test_half_full_space_particle_pairs"]
+    assert sum(len(c.intra_cell_pairs(True)) for c in cg2.iter_cells()) == g3["full_over_half_intra"] * intra
+    assert sum(len(c.inter_cell_pairs(True)) for c in cg2.iter_cells()) == g3["full_over_half_inter"] * inter
+    # the per-cell enumeration in the reference's own half space gives the device's pair set
+    host = sorted((min(p[0], q[0]), max(p[0], q[0])) for c in cg2.iter_cells() for p, q in c.particle_pairs())
+    dev = sorted((min(int(i), int(j)), max(int(i), int(j))) for i, j in cg2.particle_pairs())
+    assert host == dev
+    # query(): cell of a point (possibly empty), None when too far outside (cellgrid.rs:360-365)
+    cell = cg2.query(pts2[0])
+    assert cell is not None and any(l == 0 for l, _ in cell.iter())
+    assert cg2.query(pts2.max(0) + 5.0 * g2["cutoff"]) is None

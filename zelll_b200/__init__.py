@@ -5,6 +5,6 @@
 C ABI of include/zelll_b200.h).  There is no CPU fallback.
 """
 from ._ffi import CMP_LE, CMP_LT, CMP_NONE, ZelllB200Error  # noqa: F401
-from .cellgrid import CellGrid, CellGridIter, CellQueryIter, GridInfo  # noqa: F401
+from .cellgrid import CellGrid, CellGridIter, CellQueryIter, GridCell, GridInfo  # noqa: F401
 
-__all__ = ["CellGrid", "CellGridIter", "CellQueryIter", "GridInfo", "ZelllB200Error", "CMP_NONE", "CMP_LT", "CMP_LE"]
+__all__ = ["CellGrid", "CellGridIter", "CellQueryIter", "GridCell", "GridInfo", "ZelllB200Error", "CMP_NONE", "CMP_LT", "CMP_LE"]

@@ -145,6 +145,72 @@ class CellQueryIter:
         return j, self._coords(j)
 
 
+class GridCell:
+    """`zelll::cellgrid::GridCell` (src/cellgrid/iters.rs:121-241): a view of one (possibly empty) cell
+    over the cell-sorted storage fetched once by `CellGrid.iter_cells()` / `.query()`."""
+
+    def __init__(self, view: "_CellView", index: int):
+        self._v = view
+        self.index = int(index)  # flat cell key (iters.rs:143-146)
+
+    def iter(self):
+        """Particles of this cell as (label, [coords]) (iters.rs:154-168); empty for an absent cell."""
+        k = self._v.slot.get(self.index)
+        if k is None:
+            return iter(())
+        b, c = int(self._v.begin[k]), int(self._v.count[k])
+        return ((int(self._v.labels[p]), [float(x) for x in self._v.xyz[p]]) for p in range(b, b + c))
+
+    __iter__ = iter
+
+    def __len__(self):
+        k = self._v.slot.get(self.index)
+        return 0 if k is None else int(self._v.count[k])
+
+    def neighbors(self, full: bool = False):
+        """Non-empty neighbour cells (iters.rs:197-214): Half = the first half of
+        `FlatIndex::neighbor_indices` (iters.rs:58-63), Full = all of them (iters.rs:44-56)."""
+        rel = self._v.neighbor_indices
+        if not full:
+            rel = rel[: len(rel) // 2]
+        out = []
+        for r in rel:
+            key = _wrap_i32(self.index + int(r))
+            if key in self._v.slot:
+                out.append(GridCell(self._v, key))
+        return out
+
+    def intra_cell_pairs(self, full: bool = False):
+        """iters.rs:29-36 (Half: j after i) / :48-55 (Full: all ordered pairs i != j)."""
+        ps = list(self.iter())
+        if full:
+            return [(a, b) for i, a in enumerate(ps) for j, b in enumerate(ps) if i != j]
+        return [(a, b) for i, a in enumerate(ps) for b in ps[i + 1:]]
+
+    def inter_cell_pairs(self, full: bool = False):
+        """iters.rs:228-231: this cell x the particles of its neighbour cells."""
+        others = [q for cell in self.neighbors(full) for q in cell.iter()]
+        return [(p, q) for p in self.iter() for q in others]
+
+    def particle_pairs(self):
+        """iters.rs:238-241: intra::<Half> ++ inter::<Half>."""
+        return self.intra_cell_pairs(False) + self.inter_cell_pairs(False)
+
+
+def _wrap_i32(v: int) -> int:
+    return ((v + 2**31) % 2**32) - 2**31
+
+
+class _CellView:
+    """Host snapshot of the grid's CSR arrays shared by the GridCell views of one rebuild."""
+
+    def __init__(self, grid: "CellGrid"):
+        self.keys, self.begin, self.count = grid.cells()
+        self.labels, self.xyz = grid.cell_storage()
+        self.neighbor_indices = [int(v) for v in grid.neighbor_indices()]
+        self.slot = {int(k): i for i, k in enumerate(self.keys)}
+
+
 class CellGrid:
     """`zelll.CellGrid` on a B200.
 
@@ -238,6 +304,7 @@ class CellGrid:
         ptr, n, keep, lm = self._marshal(particles)
         self._check(self._lib.zb_grid_rebuild(self._h, ptr, n, self._optional(cutoff)))
         self._points, self._label_map = keep, lm
+        self._view = None
         if cutoff is not None:
             self._cutoff = float(self.dtype.type(cutoff))
 
@@ -374,6 +441,32 @@ class CellGrid:
     def __iter__(self) -> Iterator:  # python/src/lib.rs:168-170
         pairs = self.particle_pairs()
         return CellGridIter(pairs, self._coords_by_label(), self)
+
+    # -- cell-level views (src/cellgrid/iters.rs:121-290) ---------------------------------------
+    def _cell_view(self) -> _CellView:
+        v = getattr(self, "_view", None)
+        if v is None:
+            v = self._view = _CellView(self)
+        return v
+
+    def iter_cells(self):
+        """`CellGrid::iter()` (iters.rs:261-266): the non-empty cells (here in ascending key order)."""
+        v = self._cell_view()
+        return [GridCell(v, int(k)) for k in v.keys]
+
+    def par_iter_cells(self, chunks: int = 16):
+        """`CellGrid::par_iter()` (iters.rs:282-290): the same cells split into chunks to fan out over."""
+        cells = self.iter_cells()
+        k = max(1, int(chunks))
+        return [cells[i::k] for i in range(k)]
+
+    def query(self, coordinates):
+        """`CellGrid::query()` (cellgrid.rs:360-365): the (possibly empty) cell of a point, or None."""
+        info = self.info()
+        idx = info.try_cell_index(coordinates)
+        if idx is None:
+            return None
+        return GridCell(self._cell_view(), info.flatten_index(idx))
 
     # -- point queries (cellgrid.rs:360-401; python/src/lib.rs:204-241) ------------------------
     def query_neighbors_batch(self, queries, cutoff: Optional[float] = None, cmp="none"):

@@ -121,6 +121,7 @@ class ShardedCellGrid(CellGrid):
         self._check(self._lib.zb_grid_rebuild_sharded(self._h, ptr, n, lptr, self._optional(cutoff), a_inf, a_sup,
                                                       int(z_begin), int(z_end)))
         self._points, self._label_map, self._keep = keep, None, lab_keep
+        self._view = None
         if cutoff is not None:
             self._cutoff = float(self.dtype.type(cutoff))
 
@@ -176,6 +177,7 @@ class NativeSlabGrid(ShardedCellGrid):
                                                          self._optional(cutoff), int(label_offset) & 0xFFFFFFFF,
                                                          int(halo_cap), C.byref(info)))
         self._points, self._label_map = buf, None
+        self._view = None
         if cutoff is not None:
             self._cutoff = float(self.dtype.type(cutoff))
         self.slab = info
