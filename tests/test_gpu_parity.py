@@ -509,3 +509,46 @@ def test_gridcell_views_reference_counts(zb, golden):
     cell = cg2.query(pts2[0])
     assert cell is not None and any(l == 0 for l, _ in cell.iter())
     assert cg2.query(pts2.max(0) + 5.0 * g2["cutoff"]) is None
+
+
+def test_opt_in_prefilter_path_is_bit_exact():
+    """ZB_PREFILTER=1 routes f64 staged tiles through the f32 guard-band prefilter (pair_kernels.cuh);
+    its pair sets, counts and energies must be those of the exact path.  Run in a subprocess because the
+    switch is read from the environment by the library."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, sys
+sys.path.insert(0, %r)
+import oracle, zelll_b200
+from zelll_b200 import workload
+for n, kind in ((20000, "lj"), (6000, "cube"), (4000, "dense")):
+    rng = np.random.default_rng(n)
+    if kind == "lj":
+        pts, c = workload.generate_points_random(n), 10.0
+    elif kind == "cube":
+        pts, c = rng.random((n, 3)) * 11.0, 1.0
+    else:
+        pts, c = rng.random((n, 3)) * 2.0, 1.0
+    cg = zelll_b200.CellGrid(pts, c)
+    og = oracle.OracleCellGrid(pts, c)
+    for cmp, oc in (("lt", oracle.CMP_LT), ("le", oracle.CMP_LE)):
+        want = og.pairs_canonical(oc, c)
+        assert np.array_equal(oracle.canonical_pairs(cg.particle_pairs(c, cmp)), want), (kind, cmp)
+        assert cg.pair_count(c, cmp) == len(want)
+        e, m = cg.lj_energy(c, cmp, return_pairs=True)
+        _, e64, mo = og.lj_energy(oc, c)
+        assert m == mo and abs(e - e64) <= 1e-10 * abs(e64), (kind, cmp, e, e64)
+    # a filter radius below the cell size, and pairs exactly at the threshold
+    assert np.array_equal(oracle.canonical_pairs(cg.particle_pairs(0.37 * c, "le")), og.pairs_canonical(oracle.CMP_LE, 0.37 * c))
+grid = np.stack(np.meshgrid(*[np.arange(6.0)] * 3, indexing="ij"), -1).reshape(-1, 3)   # distances exactly 1
+cg = zelll_b200.CellGrid(grid, 1.0); og = oracle.OracleCellGrid(grid, 1.0)
+assert cg.pair_count(1.0, "le") == og.pair_count(oracle.CMP_LE, 1.0) > cg.pair_count(1.0, "lt") == og.pair_count(oracle.CMP_LT, 1.0)
+print("prefilter ok")
+""" % root
+    env = dict(os.environ, ZB_PREFILTER="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "prefilter ok" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
