@@ -102,3 +102,23 @@ def test_slab_bounds_partition():
             assert b[0][0] == 0 and b[-1][1] == nz
             assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
     assert grid_shape([0.2, 0.25, 0.3], [2.7, 2.75, 2.8], 1.0, np.float64) == [3, 3, 3]
+
+
+def test_workload_generators_and_lammps_writer():
+    """Synthetic workloads of the reference benches (benches/lj.rs:15-34, 59-66) and the LAMMPS data
+    layout of examples/lammps_data.rs:56-80."""
+    from zelll_b200 import workload
+
+    pts = workload.generate_points_random(1000)
+    a, b, c = workload.lj_box(1000)
+    assert (a, b) == (30.0, 30.0) and abs(c - 1000 / 9.0) < 1e-9
+    assert np.all(np.abs(pts) <= np.array([a, b, c]) / 2)
+    assert np.array_equal(pts, workload.generate_points_random(1000))             # seeded, reproducible
+    assert np.array_equal(pts[100:200], workload.generate_points_random(100, vol=(a, b, c), first=100))  # chunkable
+    srt = workload.presort_by_z(pts)
+    assert np.all(np.diff(srt[:, 2]) >= 0)
+    assert np.array_equal(workload.perturb(pts, 0, 0.0), pts)
+    text = workload.lammps_data(pts[:3]).splitlines()
+    assert text[2] == "3 atoms" and text[3] == "1 atom types"
+    assert text[4] == "-15 15 xlo xhi" and text[8] == "Atoms # atomic"
+    assert text[10].split()[:2] == ["1", "1"] and float(text[10].split()[2]) == pts[0, 0]

@@ -62,3 +62,31 @@ def perturb(points: np.ndarray, step: int, amplitude: float, seed: int = REFEREN
     n = points.shape[0]
     u = uniform01(points.size, seed ^ 0x5DEECE66D, (step + 1) * points.size).reshape(n, -1)
     return np.ascontiguousarray((points.astype(np.float64) + (2.0 * u - 1.0) * amplitude).astype(points.dtype))
+
+
+def lammps_data(points: np.ndarray, vol=None, seed: int = REFERENCE_SEED) -> str:
+    """The benchmark cloud as a LAMMPS `read_data` file, the layout of examples/lammps_data.rs:56-80
+    (for cross-checking energies against `lj/cut`, more_benches/in.zelllbench.txt, off-box)."""
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    a, b, c = lj_box(n) if vol is None else vol
+
+    def fmt(v: float) -> str:  # Rust's `{}` for f64: shortest round-trip repr, no exponent padding
+        r = repr(float(v))
+        return r[:-2] if r.endswith(".0") else r
+
+    lines = [
+        f"# {n} random atom positions taken from zelll benchmarks:",
+        f"# generate_points_random({n}, [{a!r}, {b!r}, {c!r}], [0.0, 0.0, 0.0], Some({seed}));",
+        f"{n} atoms",
+        "1 atom types",
+        f"-{fmt(0.5 * a)} {fmt(0.5 * a)} xlo xhi",
+        f"-{fmt(0.5 * b)} {fmt(0.5 * b)} ylo yhi",
+        f"-{fmt(0.5 * c)} {fmt(0.5 * c)} zlo zhi",
+        "",
+        "Atoms # atomic",
+        "# lammps read_data needs an empty line here: https://docs.lammps.org/Errors_details.html#err0016",
+    ]
+    lines += [f"{i + 1} 1 {fmt(p[0])} {fmt(p[1])} {fmt(p[2])}" for i, p in enumerate(pts)]
+    lines.append("")
+    return "\n".join(lines) + "\n"
