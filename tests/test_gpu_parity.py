@@ -552,3 +552,36 @@ print("prefilter ok")
     env = dict(os.environ, ZB_PREFILTER="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "prefilter ok" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_seeded_fuzz_against_oracle(zb):
+    """60 seeded random configurations (size, dimension, dtype, anisotropic box, clustering, cutoff,
+    filter radius, comparison): pair sets bit-exact, counts equal, energies within tolerance."""
+    rng = np.random.default_rng(20260101)
+    for case in range(60):
+        ndim = int(rng.choice([2, 3], p=[0.3, 0.7]))
+        dtype = np.float32 if rng.random() < 0.4 else np.float64
+        n = int(rng.choice([1, 2, 5, 40, 300, 1200, 3000]))
+        ext = rng.uniform(0.5, 30.0, ndim) * rng.choice([1.0, 0.05], ndim, p=[0.8, 0.2])
+        origin = rng.uniform(-50.0, 50.0, ndim)
+        pts = origin + rng.random((n, ndim)) * ext
+        if rng.random() < 0.3:  # clump a third of the particles
+            k = max(1, n // 3)
+            pts[:k] = pts[0] + rng.normal(0.0, 0.2, (k, ndim))
+        pts = pts.astype(dtype)
+        cutoff = float(rng.uniform(0.3, 4.0))
+        radius = cutoff * float(rng.choice([1.0, 0.5, 1.3, 0.9]))
+        cg = zb.CellGrid(pts, cutoff, dtype=dtype, ndim=ndim)
+        og = OracleCellGrid(pts, cutoff, dtype=dtype, ndim=ndim)
+        assert np.array_equal(cg.keys(), og.keys()), case
+        assert cg.info().shape().tolist() == og.info()["shape"], case
+        for cmp in ("none", "lt", "le"):
+            want = og.pairs_canonical(OCMP[cmp], radius)
+            assert cg.pair_count(radius, cmp) == len(want), (case, cmp)
+            assert np.array_equal(canonical_pairs(cg.particle_pairs(radius, cmp)), want), (case, cmp)
+        e_t, e64, m = og.lj_energy(CMP_LE, radius)
+        e, mm = cg.lj_energy(radius, "le", return_pairs=True)
+        assert mm == m, case
+        if np.isfinite(e64) and m:
+            rtol = F64_RTOL if dtype == np.float64 else F32_RTOL
+            assert abs(e - e64) <= rtol * abs(e64), (case, e, e64)
