@@ -318,15 +318,18 @@ def run_ours(args):
             kernels[name] = {"ms_per_launch": per, "launches": cnt, "algorithmic_GB": alg_bytes[name] * n_local / 1e9,
                              "GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
-    traffic = None
+    traffic, ncu_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+        traffic = tj.get(dom)
+        ncu_note = tj.get("_ncu_" + dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": kernels[dom]["ms_per_launch"],
                 "candidate_tests_per_s": 81.6 * n_local / (kernels[dom]["ms_per_launch"] * 1e-3) if dom == "pair_lj" else None,
+                "ncu": ncu_note,
                 "step_algorithmic_GB": 101.6 * n_local / 1e9,
                 "step_frac_of_hbm_peak": 101.6 * n_local / 1e9 / (ms_step * 1e-3) / hbm_peak}
 
