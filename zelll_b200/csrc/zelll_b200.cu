@@ -130,6 +130,8 @@ struct zb_grid {
   double* h_red = nullptr;                        // pinned mirror of `red`
   uint64_t n_local = 0, n_halo = 0;
   uint64_t build_id = 0;  // bumped by every rebuild
+  struct OccEntry { const void* kern; size_t smem; int occ; };
+  std::vector<OccEntry> occ_cache;  // launch_pairs: occupancy per (kernel, dynamic smem)
   // zb_grid_pairs: per-tile counts of the last sizing pass (still in tile_counts)
   bool emit_cache_valid = false;
   uint64_t emit_cache_build = 0, emit_cache_total = 0;
@@ -628,11 +630,18 @@ int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, t
   PairParams<T> p = p_in;
   ZB_TRY(sparse_tile_list<T>(g, pl, p));
   auto go = [&](auto kern) -> int {
-    ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    // persistent grid: one wave of resident CTAs
+    // persistent grid: one wave of resident CTAs.  The attribute / occupancy queries cost ~10 us of
+    // host time, so their result is cached per (kernel, shared-memory size).
     int occ = 0;
-    ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPairThreads, pl.smem));
-    occ = std::max(1, std::min(occ, (int)kMaxPairCtasPerSm));
+    const void* key = reinterpret_cast<const void*>(kern);
+    for (const auto& e : g->occ_cache)
+      if (e.kern == key && e.smem == pl.smem) occ = e.occ;
+    if (occ == 0) {
+      ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPairThreads, pl.smem));
+      occ = std::max(1, std::min(occ, (int)kMaxPairCtasPerSm));
+      g->occ_cache.push_back({key, pl.smem, occ});
+    }
     pl.blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * (uint32_t)occ));
     {
       StageSpan span(g, Consumer::kStage);
@@ -671,9 +680,10 @@ int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* pla
   typename CountConsumer<T>::Args a;
   a.tile_counts = per_tile ? static_cast<unsigned long long*>(g->tile_counts.p) : nullptr;
   a.block_totals = static_cast<unsigned long long*>(g->block_totals.p);
-  ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
   if (per_tile) ZB_CUDA(cudaMemsetAsync(g->tile_counts.p, 0, ((size_t)pl.ntiles + 1) * 8, g->stream));
+  // every launched block writes its slot of block_totals (finish()): clear only when nothing runs
   if (pl.ntiles) ZB_TRY((launch_pairs<T, CountConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
+  else ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
   ZB_TRY(finalize(g, false, pl.blocks));
   if (plan_out) *plan_out = pl;
   return ZB_OK;
@@ -687,9 +697,12 @@ int lj_impl(zb_grid* g, int cmp, double fc) {
   typename LjConsumer<T>::Args a;
   a.block_energy = static_cast<double*>(g->block_energy.p);
   a.block_totals = static_cast<unsigned long long*>(g->block_totals.p);
-  ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
-  ZB_CUDA(cudaMemsetAsync(g->block_energy.p, 0, (size_t)pl.blocks * 8, g->stream));
-  if (pl.ntiles) ZB_TRY((launch_pairs<T, LjConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
+  if (pl.ntiles) {
+    ZB_TRY((launch_pairs<T, LjConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
+  } else {  // every launched block writes its slots (finish()): clear only when nothing runs
+    ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
+    ZB_CUDA(cudaMemsetAsync(g->block_energy.p, 0, (size_t)pl.blocks * 8, g->stream));
+  }
   ZB_TRY(finalize(g, true, pl.blocks));
   return ZB_OK;
 }
