@@ -232,6 +232,7 @@ struct CountConsumer {
   static constexpr int kStage = 4;  // ZB_STAGE_PAIR_COUNT
   static constexpr bool kNeedLabels = false;
   static constexpr bool kCountsOnly = true;
+  static constexpr int kUnroll = kPairUnroll;  // test-loop unroll factor
   Args a;
   ConsumerSmem* cs;
   ExactCtx<T> ex;
@@ -307,6 +308,7 @@ struct EmitConsumer {
   static constexpr int kStage = 5;  // ZB_STAGE_PAIR_EMIT
   static constexpr bool kNeedLabels = true;
   static constexpr bool kCountsOnly = false;
+  static constexpr int kUnroll = 2;
   Args a;
   ConsumerSmem* cs;
   ExactCtx<T> ex;
@@ -416,6 +418,10 @@ struct LjConsumer {
   static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
   static constexpr bool kNeedLabels = false;
   static constexpr bool kCountsOnly = false;
+#ifndef ZB_LJ_UNROLL
+#define ZB_LJ_UNROLL 2
+#endif
+  static constexpr int kUnroll = ZB_LJ_UNROLL;  // keeps the kernel below ~5k SASS instructions (I-cache)
   Args a;
   ExactCtx<T> ex;
   T* q;          // exact loop: dsq; prefilter loop: uint32 (ipos << 16 | jpos) in the same bytes
@@ -578,12 +584,19 @@ __device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, co
 //   recb / csrb are biased base pointers: recb[pos] is record `pos` of the cell-sorted array and
 //   csrb[cell] its CSR entry, whether they live in shared memory (staged tile) or in global memory.
 //   Every lane keeps NJ candidates j in registers; the home particles i are broadcast loads.
-template <class T, int CMP, int NJ, class Consumer>
-__device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uint32_t m, const T (&xj)[NJ],
-                                            const T (&yj)[NJ], const T (&zj)[NJ], const uint32_t (&lj)[NJ],
-                                            const uint32_t (&thr)[NJ], T c2, Consumer& cons) {
-#pragma unroll kPairUnroll
-  for (uint32_t i = 0; i < m; ++i) {
+// P > 1 is the packed tail: the chunk has at most 32 / P candidates, the warp is split into P
+// phases (lane / (32 / P)) and phase ph tests home particles ph, ph + P, ...: the loop runs
+// ceil(m / P) times instead of m.  A phase whose particle index runs past the cell reads a
+// neighbouring record (in bounds: the stage and the record array have slack) and discards it
+// through i < thr <= m.
+template <class T, int CMP, int NJ, int P, class Consumer>
+__device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uint32_t m, uint32_t ph,
+                                            const T (&xj)[NJ], const T (&yj)[NJ], const T (&zj)[NJ],
+                                            const uint32_t (&lj)[NJ], const uint32_t (&thr)[NJ], T c2,
+                                            Consumer& cons) {
+#pragma unroll Consumer::kUnroll
+  for (uint32_t ib = 0; ib < m; ib += P) {
+    const uint32_t i = P == 1 ? ib : ib + ph;
     T xi, yi, zi;
     uint32_t li;
     load_part<Consumer::kNeedLabels>(home + i, xi, yi, zi, li);
@@ -603,50 +616,53 @@ __device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uin
   }
 }
 
+// one group of up to 32 NJ candidates (lane l holds candidates kb + 32 q + l), or -- P > 1 -- a
+// packed tail of up to 32 / P candidates (lane l holds candidate kb + l % (32 / P))
+template <class T, int CMP, int NJ, int P, class Consumer>
+__device__ __forceinline__ void process_group(const CellRuns& r, const Rec<T>* __restrict__ recb, uint32_t kb, T c2,
+                                              Consumer& cons) {
+  constexpr uint32_t W = 32 / P;
+  const unsigned lane = lane_id();
+  const uint32_t slot = P == 1 ? lane : (lane & (W - 1)), ph = P == 1 ? 0u : lane / W;
+  T xj[NJ], yj[NJ], zj[NJ];
+  uint32_t lj[NJ], thr[NJ];
+#pragma unroll
+  for (int q = 0; q < NJ; ++q) {
+    const uint32_t k = kb + 32u * q + slot;
+    thr[q] = r.thr(k);
+    load_part<Consumer::kNeedLabels>(recb + r.pos(k), xj[q], yj[q], zj[q], lj[q]);
+  }
+  exact_tests<T, CMP, NJ, P>(recb + r.hb, r.m, ph, xj, yj, zj, lj, thr, c2, cons);
+  cons.chunk_end();
+}
+
 template <class T, int CMP, class Consumer>
 __device__ __forceinline__ void process_cell(const CellRuns& r, const Rec<T>* __restrict__ recb, T c2, Consumer& cons) {
   constexpr int NJMAX = GenericNJ<T>::value;
   if (r.m == 0) return;
-  const unsigned lane = lane_id();
-  const Rec<T>* home = recb + r.hb;
-  for (uint32_t kb = 0; kb < r.K; kb += 32 * NJMAX) {
-    T xj[NJMAX], yj[NJMAX], zj[NJMAX];
-    uint32_t lj[NJMAX], thr[NJMAX];
+  if (CMP == 0 && Consumer::kCountsOnly) {  // unfiltered count: no per-pair work
+    const unsigned lane = lane_id();
     uint32_t sum_thr = 0;
-#pragma unroll
-    for (int q = 0; q < NJMAX; ++q) {
-      const uint32_t k = kb + 32u * q + lane;
-      thr[q] = r.thr(k);
-      sum_thr += thr[q];
-      if (!(CMP == 0 && Consumer::kCountsOnly) && kb + 32u * q < r.K)
-        load_part<Consumer::kNeedLabels>(recb + r.pos(k), xj[q], yj[q], zj[q], lj[q]);
+    for (uint32_t kb = 0; kb < r.K; kb += 32) sum_thr += r.thr(kb + lane);
+    cons.add(sum_thr);
+    return;
+  }
+  uint32_t kb = 0;
+  while (kb < r.K) {
+    const uint32_t rem = r.K - kb;
+    if (NJMAX >= 2 && rem > 48) {          // two full-ish slots: one broadcast load per 2 tests
+      process_group<T, CMP, 2, 1>(r, recb, kb, c2, cons);
+      kb += 64;
+    } else if (rem > 16) {                 // one slot (a 33..48 remainder leaves a packed tail behind)
+      process_group<T, CMP, 1, 1>(r, recb, kb, c2, cons);
+      kb += 32;
+    } else if (rem > 8) {                  // <= 16 candidates: two phases of 16 lanes
+      process_group<T, CMP, 1, 2>(r, recb, kb, c2, cons);
+      kb += 16;
+    } else {                               // <= 8 candidates: four phases of 8 lanes
+      process_group<T, CMP, 1, 4>(r, recb, kb, c2, cons);
+      kb += 8;
     }
-    if (CMP == 0 && Consumer::kCountsOnly) {
-      cons.add(sum_thr);  // unfiltered count: no per-pair work
-      continue;
-    }
-    const uint32_t nj = min((r.K - kb + 31u) >> 5, (uint32_t)NJMAX);
-    // specialise on the number of live candidate slots (warp-uniform) so idle slots cost nothing
-    auto run = [&](auto tag) {
-      constexpr int NJ = decltype(tag)::value;
-      T x[NJ], y[NJ], z[NJ];
-      uint32_t l[NJ], t[NJ];
-#pragma unroll
-      for (int q = 0; q < NJ; ++q) { x[q] = xj[q]; y[q] = yj[q]; z[q] = zj[q]; l[q] = lj[q]; t[q] = thr[q]; }
-      exact_tests<T, CMP, NJ>(home, r.m, x, y, z, l, t, c2, cons);
-    };
-    if constexpr (NJMAX == 1) {
-      run(IntTag<1>());
-    } else if constexpr (NJMAX == 2) {
-      if (nj == 1) run(IntTag<1>());
-      else run(IntTag<2>());
-    } else {
-      if (nj == 1) run(IntTag<1>());
-      else if (nj == 2) run(IntTag<2>());
-      else if (nj == 3) run(IntTag<3>());
-      else run(IntTag<4>());
-    }
-    cons.chunk_end();
   }
 }
 
