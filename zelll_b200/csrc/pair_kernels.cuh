@@ -53,6 +53,9 @@ namespace zb {
 constexpr int kPairThreads = ZB_PAIR_THREADS;
 constexpr int kPairUnroll = ZB_PAIR_UNROLL;
 constexpr int kMaxNJ = 4;  // candidates held in registers per lane (register tile of the cell loop)
+#ifndef ZB_LJ_FUSE
+#define ZB_LJ_FUSE 2  // home particles per LJ compaction step (measured: 2 = 3 > 4 > 1)
+#endif
 constexpr int kQueueSlots = 32 + 32 * kMaxNJ;  // per-warp hit queue: one full row + one iteration's worth
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kStageCells = 512;  // staged CSR entries per tile (cells + halo + 1)
@@ -233,6 +236,7 @@ struct CountConsumer {
   static constexpr bool kNeedLabels = false;
   static constexpr bool kCountsOnly = true;
   static constexpr int kUnroll = kPairUnroll;  // test-loop unroll factor
+  static constexpr int kFuse = 1;              // home particles handed to test_n per call
   Args a;
   ConsumerSmem* cs;
   ExactCtx<T> ex;
@@ -250,7 +254,8 @@ struct CountConsumer {
     ex.rec = staged;
   }
   template <int NJ>
-  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], uint32_t, const uint32_t (&)[NJ]) {
+  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], const uint32_t (&)[NJ],
+                                         const uint32_t (&)[NJ]) {
 #pragma unroll
     for (int q = 0; q < NJ; ++q) c32 += h[q] ? 1u : 0u;
   }
@@ -304,11 +309,12 @@ struct EmitConsumer {
     const unsigned long long* tile_offsets;  // [ntiles + 1]
     uint2* out;
   };
-  static constexpr int kWarpSmemBytes = kQueueSlots * sizeof(uint2);
+  static constexpr int kWarpSmemBytes = (32 + 32 * kMaxNJ * 2) * sizeof(uint2);  // one row + one fused step
   static constexpr int kStage = 5;  // ZB_STAGE_PAIR_EMIT
   static constexpr bool kNeedLabels = true;
   static constexpr bool kCountsOnly = false;
   static constexpr int kUnroll = 2;
+  static constexpr int kFuse = 2;
   Args a;
   ConsumerSmem* cs;
   ExactCtx<T> ex;
@@ -358,11 +364,12 @@ struct EmitConsumer {
     put(h, make_uint2(la, lb));
   }
   template <int NJ>
-  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], uint32_t li, const uint32_t (&lj)[NJ]) {
+  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], const uint32_t (&li)[NJ],
+                                         const uint32_t (&lj)[NJ]) {
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
       const unsigned b = __ballot_sync(0xffffffffu, h[k]);
-      if (h[k]) q[qn + __popc(b & ltmask)] = make_uint2(li, lj[k]);
+      if (h[k]) q[qn + __popc(b & ltmask)] = make_uint2(li[k], lj[k]);
       qn += __popc(b);
     }
     drain_exact_rows();
@@ -412,7 +419,7 @@ struct LjConsumer {
     unsigned long long* block_totals;   // [gridDim.x]
   };
   // exact loop: (32 + 32 NJ) dsq values; prefilter loop (f64 only): kQueueSlots packed positions
-  static constexpr int kExactBytes = (32 + 32 * GenericNJ<T>::value) * (int)sizeof(T);
+  static constexpr int kExactBytes = (32 + 32 * GenericNJ<T>::value * ZB_LJ_FUSE) * (int)sizeof(T);
   static constexpr int kPfBytes = sizeof(T) == 8 ? kQueueSlots * 4 : 0;
   static constexpr int kWarpSmemBytes = kExactBytes > kPfBytes ? kExactBytes : kPfBytes;
   static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
@@ -422,6 +429,9 @@ struct LjConsumer {
 #define ZB_LJ_UNROLL 2
 #endif
   static constexpr int kUnroll = ZB_LJ_UNROLL;  // keeps the kernel below ~5k SASS instructions (I-cache)
+  // 2 home particles per compaction step: their distance tests are independent instruction chains
+  // that overlap, and the queue bookkeeping / drain check is paid once for both
+  static constexpr int kFuse = ZB_LJ_FUSE;
   Args a;
   ExactCtx<T> ex;
   T* q;          // exact loop: dsq; prefilter loop: uint32 (ipos << 16 | jpos) in the same bytes
@@ -454,23 +464,22 @@ struct LjConsumer {
     }
   }
   template <int NJ>
-  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&dsq)[NJ], uint32_t, const uint32_t (&)[NJ]) {
+  __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&dsq)[NJ], const uint32_t (&)[NJ],
+                                         const uint32_t (&)[NJ]) {
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
       const unsigned b = __ballot_sync(0xffffffffu, h[k]);
       if (h[k]) q[qn + __popc(b & ltmask)] = dsq[k];
       qn += __popc(b);
     }
-    // at most NJ rows can have filled up
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      if (qn >= 32) {
-        __syncwarp();
-        qn -= 32;
-        acc += (double)lj_term(q[qn + lane_id()]);
-        cnt += 1;
-        __syncwarp();
-      }
+    // at most NJ rows can have filled up; one copy of the lj code (the kernel must stay small)
+#pragma unroll 1
+    while (qn >= 32) {
+      __syncwarp();
+      qn -= 32;
+      acc += (double)lj_term(q[qn + lane_id()]);
+      cnt += 1;
+      __syncwarp();
     }
   }
   template <int CMP, int NJ>
@@ -594,14 +603,10 @@ __device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uin
                                             const T (&xj)[NJ], const T (&yj)[NJ], const T (&zj)[NJ],
                                             const uint32_t (&lj)[NJ], const uint32_t (&thr)[NJ], T c2,
                                             Consumer& cons) {
-#pragma unroll Consumer::kUnroll
-  for (uint32_t ib = 0; ib < m; ib += P) {
-    const uint32_t i = P == 1 ? ib : ib + ph;
+  constexpr int F = Consumer::kFuse;  // home particles per consumer call
+  auto test = [&](uint32_t i, bool* h, T* dsq, uint32_t& li) {
     T xi, yi, zi;
-    uint32_t li;
     load_part<Consumer::kNeedLabels>(home + i, xi, yi, zi, li);
-    bool h[NJ];
-    T dsq[NJ];
 #pragma unroll
     for (int q = 0; q < NJ; ++q) {
       h[q] = i < thr[q];
@@ -612,7 +617,28 @@ __device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uin
         h[q] = h[q] && passes<CMP>(dsq[q], c2);
       }
     }
-    cons.template test_n<NJ>(h, dsq, li, lj);
+  };
+  // F home particles per consumer call: their distance tests are independent instruction chains
+  // that overlap, and the consumer's bookkeeping is paid once.  Indices past the cell (i >= m >=
+  // thr) never hit; the reads stay in bounds (see above).
+  uint32_t ljf[NJ * F];
+#pragma unroll
+  for (int f = 0; f < F; ++f)
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) ljf[f * NJ + q] = lj[q];
+#pragma unroll Consumer::kUnroll
+  for (uint32_t ib = 0; ib < m; ib += F * P) {
+    bool h[NJ * F];
+    T dsq[NJ * F];
+    uint32_t lif[NJ * F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      uint32_t li;
+      test((P == 1 ? ib : ib + ph) + f * P, h + f * NJ, dsq + f * NJ, li);
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) lif[f * NJ + q] = li;
+    }
+    cons.template test_n<NJ * F>(h, dsq, lif, ljf);
   }
 }
 

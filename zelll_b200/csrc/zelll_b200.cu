@@ -339,9 +339,9 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n) {
       return fail(g, ZB_ERR_GRID_TOO_LARGE, "dense cell table of %zu cells does not fit device memory", (size_t)nc);
   }
   ZB_TRY(reserve(g, g->table, table_elems * 4));
-  // + 4 records of slack: the packed tail of the pair kernels may read (and discard) up to 3 records
+  // + 16 records of slack: the packed / fused test loops of the pair kernels may read (and discard) up to 15 records
   // past a home cell
-  ZB_TRY(reserve(g, g->sorted, ((size_t)n + 4) * sizeof(Rec<T>)));
+  ZB_TRY(reserve(g, g->sorted, ((size_t)n + 16) * sizeof(Rec<T>)));
   const uint32_t ntile = (uint32_t)((nc + kScanTile - 1) / kScanTile);
   ZB_TRY(reserve(g, g->scan_state, (size_t)ntile * sizeof(unsigned long long)));
 
