@@ -95,6 +95,13 @@ const char* zb_last_error(const zb_grid* g);
  * cell-sorted buffer (cellgrid.rs:196-231, storage.rs:77-81, 106-111). */
 int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutoff_or_null);
 
+/* Double buffering for callers that stream frames from HOST memory (trajectory analysis): starts the
+ * host-to-device copy of the NEXT rebuild's input on a private copy stream and returns at once, so
+ * the copy overlaps the pair / LJ kernels of the current grid.  A following zb_grid_rebuild with
+ * the same (xyz, n) uses the staged copy instead of copying again.  xyz should be pinned memory
+ * (pageable memory makes the copy synchronous); the caller must not modify it until that rebuild. */
+int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n);
+
 /* Slab-sharded rebuild for multi-GPU runs (no counterpart upstream):
  * the bounding box is IMPOSED (the all-reduced global Aabb) so every rank derives the same
  * GridInfo and hence the same keys as a single-GPU grid; `xyz` holds this rank's particles of

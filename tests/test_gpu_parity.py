@@ -585,3 +585,23 @@ def test_seeded_fuzz_against_oracle(zb):
         if np.isfinite(e64) and m:
             rtol = F64_RTOL if dtype == np.float64 else F32_RTOL
             assert abs(e - e64) <= rtol * abs(e64), (case, e, e64)
+
+
+def test_prefetch_double_buffering(zb):
+    """zb_grid_prefetch: the staged copy of the next frame is what the following rebuild consumes."""
+    import torch
+
+    frames = [torch.from_numpy(workload.generate_points_random(30000, seed=s)).pin_memory() for s in (1, 2, 3)]
+    cg = zb.CellGrid(frames[0].numpy(), 10.0)
+    want = [OracleCellGrid(f.numpy(), 10.0).lj_energy(CMP_LT, 10.0) for f in frames]
+    cg.prefetch(frames[0].numpy())
+    for k in range(6):
+        cur, nxt = frames[k % 3].numpy(), frames[(k + 1) % 3].numpy()
+        cg.rebuild_mut(cur, None)
+        cg.prefetch(nxt)
+        e, m = cg.lj_energy(10.0, "lt", return_pairs=True)
+        assert m == want[k % 3][2] and abs(e - want[k % 3][1]) <= F64_RTOL * abs(want[k % 3][1])
+    cg.prefetch(frames[0].numpy())
+    cg.rebuild(frames[1].numpy())  # a different array than the prefetched one: copied normally
+    e, m = cg.lj_energy(10.0, "lt", return_pairs=True)
+    assert m == want[1][2]

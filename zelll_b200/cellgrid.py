@@ -308,6 +308,16 @@ class CellGrid:
         if cutoff is not None:
             self._cutoff = float(self.dtype.type(cutoff))
 
+    def prefetch(self, particles) -> None:
+        """Start copying the NEXT rebuild's (pinned) host input to the device while this grid is still being
+        consumed; `rebuild(particles)` with the same array then finds it resident (zb_grid_prefetch)."""
+        if isinstance(particles, np.ndarray):
+            a = np.ascontiguousarray(particles, dtype=self.dtype).reshape(-1, self.ndim)
+            if a.ctypes.data != particles.ctypes.data:
+                return  # a converted copy would not be the array rebuild() sees
+            if a.shape[0]:
+                self._check(self._lib.zb_grid_prefetch(self._h, a.ctypes.data, a.shape[0]))
+
     def rebuild_mut(self, particles, cutoff: Optional[float] = None) -> None:
         """`CellGrid::rebuild_mut(&mut self, particles, Option<T>)` (cellgrid.rs:264-312)."""
         self.rebuild(particles, cutoff)

@@ -96,6 +96,11 @@ struct zb_grid {
 
   // device memory, grown on demand and reused across rebuilds (rebuild_mut contract)
   DevBuf in;        // staged input when the caller passes host memory
+  DevBuf in_next;   // zb_grid_prefetch: the NEXT rebuild's input, copied while this grid is being consumed
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done = nullptr, build_done = nullptr;
+  const void* prefetched_host = nullptr;
+  uint64_t prefetched_n = 0;
   DevBuf labels_in; // staged labels (sharded, host labels)
   DevBuf table;     // uint32 [4 + ncells + pad]; csr = table + 3, cursor = table + 4
   DevBuf sorted;    // Rec<T>[n]
@@ -415,6 +420,14 @@ int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
     *dev = xyz;
     return ZB_OK;
   }
+  if (g->prefetched_host == xyz && g->prefetched_n == n && g->in_next.p) {
+    // the copy was started by zb_grid_prefetch on the copy stream: wait for it on the device, no host stall
+    ZB_CUDA(cudaStreamWaitEvent(g->stream, g->copy_done, 0));
+    std::swap(g->in, g->in_next);
+    g->prefetched_host = nullptr;
+    *dev = g->in.p;
+    return ZB_OK;
+  }
   ZB_TRY(reserve(g, g->in, bytes));
   ZB_CUDA(cudaMemcpyAsync(g->in.p, xyz, bytes, cudaMemcpyHostToDevice, g->stream));
   *dev = g->in.p;
@@ -516,6 +529,7 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   if (g->track_keys && !sharded)
     ZB_CUDA(cudaMemcpyAsync(&g->h_misc->keys_changed, &g->misc->keys_changed, sizeof(int), cudaMemcpyDeviceToHost,
                             g->stream));
+  if (g->build_done) ZB_CUDA(cudaEventRecord(g->build_done, g->stream));  // the input buffer is free again
   ZB_CUDA(cudaStreamSynchronize(g->stream));
   if (slab_check) {
     g->slab_check_pending = false;
@@ -791,11 +805,14 @@ void zb_grid_destroy(zb_grid* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
+  DevBuf* bufs[] = {&g->in,        &g->in_next,     &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
                     &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->halo_send, &g->halo_recv, &g->halo_labels,
                     &g->red};
   for (DevBuf* b : bufs) free_buf(*b);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+  if (g->copy_done) cudaEventDestroy(g->copy_done);
+  if (g->build_done) cudaEventDestroy(g->build_done);
   if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
   if (g->nccl.dl) dlclose(g->nccl.dl);
   if (g->h_red) cudaFreeHost(g->h_red);
@@ -833,6 +850,35 @@ int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutof
   ZB_TRY(enter(g));
   return g->dtype == ZB_F32 ? rebuild_impl<float>(g, xyz, n, nullptr, cutoff_or_null, nullptr, nullptr, 0, 0, false)
                             : rebuild_impl<double>(g, xyz, n, nullptr, cutoff_or_null, nullptr, nullptr, 0, 0, false);
+}
+
+int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n) {
+  ZB_TRY(enter(g));
+  if (n == 0 || !xyz_host) return fail(g, ZB_ERR_BAD_ARG, "nothing to prefetch");
+  if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
+  if (is_device_ptr(xyz_host)) return ZB_OK;  // already resident
+  if (!g->copy_stream) {
+    ZB_CUDA(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    ZB_CUDA(cudaEventCreateWithFlags(&g->copy_done, cudaEventDisableTiming));
+    ZB_CUDA(cudaEventCreateWithFlags(&g->build_done, cudaEventDisableTiming));
+  }
+  const size_t bytes = (size_t)n * g->ndim * elem_size(g);
+  if (bytes > g->in_next.cap || !g->in_next.p) {
+    ZB_CUDA(cudaStreamSynchronize(g->copy_stream));
+    if (g->in_next.p) ZB_CUDA(cudaFree(g->in_next.p));
+    g->in_next.p = nullptr;
+    g->in_next.cap = 0;
+    ZB_CUDA(cudaMalloc(&g->in_next.p, bytes));
+    g->in_next.cap = bytes;
+  }
+  // in_next was the input of the build before last: its kernels are long done, but order the copy
+  // behind the last build anyway
+  ZB_CUDA(cudaStreamWaitEvent(g->copy_stream, g->build_done, 0));
+  ZB_CUDA(cudaMemcpyAsync(g->in_next.p, xyz_host, bytes, cudaMemcpyHostToDevice, g->copy_stream));
+  ZB_CUDA(cudaEventRecord(g->copy_done, g->copy_stream));
+  g->prefetched_host = xyz_host;
+  g->prefetched_n = n;
+  return ZB_OK;
 }
 
 int zb_grid_rebuild_sharded(zb_grid* g, const void* xyz, uint64_t n, const uint32_t* labels_or_null,
