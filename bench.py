@@ -245,8 +245,8 @@ def run_ours(args):
         def step_e2e():
             k = state["k"]
             state["k"] = k + 1
-            grid.rebuild_mut(frames[k % 2], None)            # finds the prefetched copy (else copies itself)
-            grid.prefetch(frames[(k + 1) % 2])               # H2D of the next frame, overlapping the LJ pass
+            grid.prefetch(frames[(k + 1) % 2])               # H2D of the next frame, overlapping this step's kernels
+            grid.rebuild_mut(frames[k % 2], None)            # finds its own frame staged (else copies itself)
             return grid.lj_energy(CUTOFF, "lt", return_pairs=True)  # host doubles: D2H inside the call
 
         engine = grid
@@ -278,9 +278,9 @@ def run_ours(args):
             state["k"] = k + 1
             cur, nxt = bufs[k % 2], bufs[(k + 1) % 2]
             stream.wait_stream(copy_stream)                  # this step's H2D has landed
+            with torch.cuda.stream(copy_stream):             # next frame's H2D overlaps this step's kernels
+                nxt[:n_per].copy_(pinned, non_blocking=True) # (nxt was read by the build before last: done)
             dg.rebuild_slab_local(cur, n_per, CUTOFF, label_offset=rank * n_per)
-            with torch.cuda.stream(copy_stream):             # next frame's H2D overlaps the LJ pass
-                nxt[:n_per].copy_(pinned, non_blocking=True)
             return dg.lj_energy_allreduce(CUTOFF, "lt", return_pairs=True)
 
     engine.use_stream(stream.cuda_stream)

@@ -96,9 +96,10 @@ const char* zb_last_error(const zb_grid* g);
 int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutoff_or_null);
 
 /* Double buffering for callers that stream frames from HOST memory (trajectory analysis): starts the
- * host-to-device copy of the NEXT rebuild's input on a private copy stream and returns at once, so
- * the copy overlaps the pair / LJ kernels of the current grid.  A following zb_grid_rebuild with
- * the same (xyz, n) uses the staged copy instead of copying again.  xyz should be pinned memory
+ * host-to-device copy of a LATER rebuild's input on a private copy stream and returns at once, so
+ * the copy overlaps the build / pair / LJ kernels of the current frame (two staging slots: call it
+ * for frame k+1 before zb_grid_rebuild of frame k).  A zb_grid_rebuild with the same (xyz, n) uses
+ * the staged copy instead of copying again.  xyz should be pinned memory
  * (pageable memory makes the copy synchronous); the caller must not modify it until that rebuild. */
 int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n);
 

@@ -96,11 +96,17 @@ struct zb_grid {
 
   // device memory, grown on demand and reused across rebuilds (rebuild_mut contract)
   DevBuf in;        // staged input when the caller passes host memory
-  DevBuf in_next;   // zb_grid_prefetch: the NEXT rebuild's input, copied while this grid is being consumed
+  // zb_grid_prefetch: two staging slots filled on a private copy stream; a rebuild whose (host
+  // pointer, n) matches a filled slot consumes it without copying
+  struct Prefetch {
+    DevBuf buf;
+    const void* host = nullptr;   // non-null: the slot holds (or is receiving) this array
+    uint64_t n = 0;
+    cudaEvent_t copied = nullptr; // recorded on the copy stream after the H2D
+    cudaEvent_t released = nullptr; // recorded on the main stream after the build that read the slot
+  } pre[2];
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copy_done = nullptr, build_done = nullptr;
-  const void* prefetched_host = nullptr;
-  uint64_t prefetched_n = 0;
+  int pre_in_use = -1;            // slot the current / last build read from
   DevBuf labels_in; // staged labels (sharded, host labels)
   DevBuf table;     // uint32 [4 + ncells + pad]; csr = table + 3, cursor = table + 4
   DevBuf sorted;    // Rec<T>[n]
@@ -420,13 +426,16 @@ int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
     *dev = xyz;
     return ZB_OK;
   }
-  if (g->prefetched_host == xyz && g->prefetched_n == n && g->in_next.p) {
-    // the copy was started by zb_grid_prefetch on the copy stream: wait for it on the device, no host stall
-    ZB_CUDA(cudaStreamWaitEvent(g->stream, g->copy_done, 0));
-    std::swap(g->in, g->in_next);
-    g->prefetched_host = nullptr;
-    *dev = g->in.p;
-    return ZB_OK;
+  for (int k = 0; k < 2; ++k) {
+    auto& sl = g->pre[k];
+    if (sl.host == xyz && sl.n == n && sl.buf.p) {
+      // the copy was started by zb_grid_prefetch on the copy stream: wait for it on the device
+      ZB_CUDA(cudaStreamWaitEvent(g->stream, sl.copied, 0));
+      sl.host = nullptr;  // consumed (the slot stays reserved until `released` fires)
+      g->pre_in_use = k;
+      *dev = sl.buf.p;
+      return ZB_OK;
+    }
   }
   ZB_TRY(reserve(g, g->in, bytes));
   ZB_CUDA(cudaMemcpyAsync(g->in.p, xyz, bytes, cudaMemcpyHostToDevice, g->stream));
@@ -529,7 +538,10 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   if (g->track_keys && !sharded)
     ZB_CUDA(cudaMemcpyAsync(&g->h_misc->keys_changed, &g->misc->keys_changed, sizeof(int), cudaMemcpyDeviceToHost,
                             g->stream));
-  if (g->build_done) ZB_CUDA(cudaEventRecord(g->build_done, g->stream));  // the input buffer is free again
+  if (g->pre_in_use >= 0) {  // the staging slot this build read is free again
+    ZB_CUDA(cudaEventRecord(g->pre[g->pre_in_use].released, g->stream));
+    g->pre_in_use = -1;
+  }
   ZB_CUDA(cudaStreamSynchronize(g->stream));
   if (slab_check) {
     g->slab_check_pending = false;
@@ -805,14 +817,17 @@ void zb_grid_destroy(zb_grid* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  DevBuf* bufs[] = {&g->in,        &g->in_next,     &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
+  DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
                     &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->halo_send, &g->halo_recv, &g->halo_labels,
                     &g->red};
   for (DevBuf* b : bufs) free_buf(*b);
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
-  if (g->copy_done) cudaEventDestroy(g->copy_done);
-  if (g->build_done) cudaEventDestroy(g->build_done);
+  for (auto& sl : g->pre) {
+    if (sl.copied) cudaEventDestroy(sl.copied);
+    if (sl.released) cudaEventDestroy(sl.released);
+    free_buf(sl.buf);
+  }
   if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
   if (g->nccl.dl) dlclose(g->nccl.dl);
   if (g->h_red) cudaFreeHost(g->h_red);
@@ -859,25 +874,34 @@ int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n) {
   if (is_device_ptr(xyz_host)) return ZB_OK;  // already resident
   if (!g->copy_stream) {
     ZB_CUDA(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
-    ZB_CUDA(cudaEventCreateWithFlags(&g->copy_done, cudaEventDisableTiming));
-    ZB_CUDA(cudaEventCreateWithFlags(&g->build_done, cudaEventDisableTiming));
+    for (auto& sl : g->pre) {
+      ZB_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+      ZB_CUDA(cudaEventCreateWithFlags(&sl.released, cudaEventDisableTiming));
+    }
   }
+  // a slot that already holds this array is refreshed; else take a slot that holds nothing pending
+  int k = -1;
+  for (int j = 0; j < 2; ++j)
+    if (g->pre[j].host == xyz_host && g->pre[j].n == n) k = j;
+  for (int j = 0; j < 2 && k < 0; ++j)
+    if (g->pre[j].host == nullptr && j != g->pre_in_use) k = j;
+  if (k < 0) return fail(g, ZB_ERR_CAPACITY, "both prefetch slots hold frames that no rebuild has consumed yet");
+  auto& sl = g->pre[k];
   const size_t bytes = (size_t)n * g->ndim * elem_size(g);
-  if (bytes > g->in_next.cap || !g->in_next.p) {
+  if (bytes > sl.buf.cap || !sl.buf.p) {
     ZB_CUDA(cudaStreamSynchronize(g->copy_stream));
-    if (g->in_next.p) ZB_CUDA(cudaFree(g->in_next.p));
-    g->in_next.p = nullptr;
-    g->in_next.cap = 0;
-    ZB_CUDA(cudaMalloc(&g->in_next.p, bytes));
-    g->in_next.cap = bytes;
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    if (sl.buf.p) ZB_CUDA(cudaFree(sl.buf.p));
+    sl.buf.p = nullptr;
+    sl.buf.cap = 0;
+    ZB_CUDA(cudaMalloc(&sl.buf.p, bytes));
+    sl.buf.cap = bytes;
   }
-  // in_next was the input of the build before last: its kernels are long done, but order the copy
-  // behind the last build anyway
-  ZB_CUDA(cudaStreamWaitEvent(g->copy_stream, g->build_done, 0));
-  ZB_CUDA(cudaMemcpyAsync(g->in_next.p, xyz_host, bytes, cudaMemcpyHostToDevice, g->copy_stream));
-  ZB_CUDA(cudaEventRecord(g->copy_done, g->copy_stream));
-  g->prefetched_host = xyz_host;
-  g->prefetched_n = n;
+  ZB_CUDA(cudaStreamWaitEvent(g->copy_stream, sl.released, 0));  // the build that last read this slot is done
+  ZB_CUDA(cudaMemcpyAsync(sl.buf.p, xyz_host, bytes, cudaMemcpyHostToDevice, g->copy_stream));
+  ZB_CUDA(cudaEventRecord(sl.copied, g->copy_stream));
+  sl.host = xyz_host;
+  sl.n = n;
   return ZB_OK;
 }
 
