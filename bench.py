@@ -192,6 +192,24 @@ def slab_points(torch, rank: int, world: int, n_per: int, device, spare: int):
     return buf
 
 
+def _bind_to_gpu_numa_node(index: int) -> None:
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) so that the pinned host
+    buffers it allocates -- and the H2D traffic of the e2e leg -- stay on the GPU's NUMA node."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass  # affinity is an optimisation only
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -209,6 +227,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: zelll_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    _bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: keeps the host frames NUMA-local
     distributed = world > 1
     if distributed:
         dist.init_process_group("nccl", device_id=device)

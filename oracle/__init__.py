@@ -31,9 +31,26 @@ class _Info(C.Structure):
     ]
 
 
+def _native_name() -> str:
+    """-march=native code only runs on the CPU it was built for: key the file by the CPU's flags."""
+    import hashlib
+
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("flags", "model name")):
+                    flags += line
+                    if line.startswith("flags"):
+                        break
+    except OSError:
+        pass
+    return "libzelll_oracle_native_%s.so" % hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
 def build(native: bool = False, quiet: bool = True) -> str:
     """Compile the oracle with the committed Makefile; returns the path of the .so."""
-    target = "libzelll_oracle_native.so" if native else "libzelll_oracle.so"
+    target = _native_name() if native else "libzelll_oracle.so"
     subprocess.run(
         ["make", "-C", _HERE, target],
         check=True,
@@ -47,7 +64,7 @@ _LIBS: dict[str, C.CDLL] = {}
 
 
 def load(native: bool = False) -> C.CDLL:
-    name = "libzelll_oracle_native.so" if native else "libzelll_oracle.so"
+    name = _native_name() if native else "libzelll_oracle.so"
     if name in _LIBS:
         return _LIBS[name]
     path = os.path.join(_HERE, name)
