@@ -102,6 +102,8 @@ int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutof
  * the staged copy instead of copying again.  xyz should be pinned memory
  * (pageable memory makes the copy synchronous); the caller must not modify it until that rebuild. */
 int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n);
+/* Orders the handle's stream behind every copy zb_grid_prefetch has started (no host stall). */
+int zb_grid_prefetch_wait(zb_grid* g);
 
 /* Slab-sharded rebuild for multi-GPU runs (no counterpart upstream):
  * the bounding box is IMPOSED (the all-reduced global Aabb) so every rank derives the same

@@ -62,6 +62,7 @@ SIGNATURES = {
     "zb_last_error": (C.c_char_p, [_vp]),
     "zb_grid_rebuild": (_int, [_vp, _vp, _u64, _dp]),
     "zb_grid_prefetch": (_int, [_vp, _vp, _u64]),
+    "zb_grid_prefetch_wait": (_int, [_vp]),
     "zb_grid_rebuild_sharded": (_int, [_vp, _vp, _u64, _vp, _dp, _dp, _dp, _i64, _i64]),
     "zb_aabb": (_int, [_vp, _vp, _u64, _dp]),
     "zb_layer_of": (_int, [_vp, _vp, _u64, _dbl, _dbl, _int, _vp]),

@@ -318,6 +318,10 @@ class CellGrid:
             if a.shape[0]:
                 self._check(self._lib.zb_grid_prefetch(self._h, a.ctypes.data, a.shape[0]))
 
+    def prefetch_wait(self) -> None:
+        """Order this grid's stream behind the copies `prefetch` has started (zb_grid_prefetch_wait)."""
+        self._check(self._lib.zb_grid_prefetch_wait(self._h))
+
     def rebuild_mut(self, particles, cutoff: Optional[float] = None) -> None:
         """`CellGrid::rebuild_mut(&mut self, particles, Option<T>)` (cellgrid.rs:264-312)."""
         self.rebuild(particles, cutoff)

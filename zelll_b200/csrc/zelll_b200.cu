@@ -905,6 +905,13 @@ int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n) {
   return ZB_OK;
 }
 
+int zb_grid_prefetch_wait(zb_grid* g) {
+  ZB_TRY(enter(g));
+  for (auto& sl : g->pre)
+    if (sl.host && sl.copied) ZB_CUDA(cudaStreamWaitEvent(g->stream, sl.copied, 0));
+  return ZB_OK;
+}
+
 int zb_grid_rebuild_sharded(zb_grid* g, const void* xyz, uint64_t n, const uint32_t* labels_or_null,
                             const double* cutoff_or_null, const double* inf, const double* sup, int64_t z_begin,
                             int64_t z_end) {
