@@ -15,7 +15,7 @@ numpy arrays (host) or torch CUDA tensors (device, zero-copy).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, Iterator, Optional, Sequence
+from typing import Iterator, Optional
 
 import numpy as np
 
