@@ -141,6 +141,10 @@ struct zb_grid {
   double* h_red = nullptr;                        // pinned mirror of `red`
   uint64_t n_local = 0, n_halo = 0;
   uint64_t build_id = 0;  // bumped by every rebuild
+  // plain (unsharded, no key tracking) rebuilds return without a final host sync: the non-empty
+  // cell count arrives through this event and is collected by the first call that needs it
+  cudaEvent_t info_event = nullptr;
+  bool info_pending = false;
   struct OccEntry { const void* kern; size_t smem; int occ; };
   std::vector<OccEntry> occ_cache;  // launch_pairs: occupancy per (kernel, dynamic smem)
   // zb_grid_pairs: per-tile counts of the last sizing pass (still in tile_counts)
@@ -457,6 +461,10 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   g->built = false;
   g->build_id++;
   g->emit_cache_valid = false;
+  if (g->info_pending) {  // the previous build's counters are about to be overwritten
+    ZB_CUDA(cudaEventSynchronize(g->info_event));
+    g->info_pending = false;
+  }
   const void* dev = nullptr;
   ZB_TRY(stage_input(g, xyz_any, n, &dev));
   const T* xyz = static_cast<const T*>(dev);
@@ -541,6 +549,17 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   if (g->pre_in_use >= 0) {  // the staging slot this build read is free again
     ZB_CUDA(cudaEventRecord(g->pre[g->pre_in_use].released, g->stream));
     g->pre_in_use = -1;
+  }
+  if (!sharded && !g->track_keys) {
+    // Nothing here can fail any more: every particle lies inside its own bounding box (a NaN
+    // coordinate maps to cell 0 like Rust's `as i32`; infinities were rejected with the box), so the
+    // window flag cannot be set.  Skip the host round trip; n_cells arrives lazily (collect_info).
+    if (!g->info_event) ZB_CUDA(cudaEventCreateWithFlags(&g->info_event, cudaEventDisableTiming));
+    ZB_CUDA(cudaEventRecord(g->info_event, g->stream));
+    g->info_pending = true;
+    g->keys_changed = -1;
+    g->built = true;
+    return ZB_OK;
   }
   ZB_CUDA(cudaStreamSynchronize(g->stream));
   if (slab_check) {
@@ -636,7 +655,10 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
 // once per build so the persistent CTAs do not walk millions of empty tiles.
 template <class T>
 int sparse_tile_list(zb_grid* g, const PairPlan& pl, PairParams<T>& p) {
-  if (pl.ntiles < 4096 || g->n_cells_nonempty * 8 > (uint64_t)g->ncells) return ZB_OK;  // dense enough
+  // Sparse for certain when even n (an upper bound of the non-empty cells) is small against the
+  // cell count; otherwise the tiles are walked directly (a clumped cloud then meets empty tiles,
+  // which the kernel skips cheaply).  Needs no host-side count: rebuilds return without a sync.
+  if (pl.ntiles < 4096 || g->n * 8 > (uint64_t)g->ncells) return ZB_OK;
   ZB_TRY(reserve(g, g->tile_list, ((size_t)pl.ntiles + 1) * 4));
   uint32_t* buf = static_cast<uint32_t*>(g->tile_list.p);
   if (g->tile_list_build != g->build_id || g->tile_list_cells != pl.tile_cells) {
@@ -739,7 +761,7 @@ template <class T>
 int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev) {
   // per-tile arrays are indexed by work item: all tiles, or (sparse boxes) the listed ones
   const bool sparse = g->tile_list_build == g->build_id && g->tile_list_cells == pl.tile_cells && g->tile_list.p &&
-                      !(pl.ntiles < 4096 || g->n_cells_nonempty * 8 > (uint64_t)g->ncells);
+                      !(pl.ntiles < 4096 || g->n * 8 > (uint64_t)g->ncells);
   tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), pl.ntiles,
                                                  sparse ? static_cast<const uint32_t*>(g->tile_list.p) : nullptr,
                                                  static_cast<unsigned long long*>(g->tile_offsets.p));
@@ -750,6 +772,15 @@ int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev
   PairPlan pe = pl;
   pe.smem = pl.smem - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
   if (pl.ntiles) ZB_TRY((launch_pairs<T, EmitConsumer<T>>(g, cmp, pe, pair_params<T>(g, pl, fc), a)));
+  return ZB_OK;
+}
+
+// the non-empty cell count of a rebuild that returned without a host sync
+int collect_info(zb_grid* g) {
+  if (!g->info_pending) return ZB_OK;
+  ZB_CUDA(cudaEventSynchronize(g->info_event));
+  g->info_pending = false;
+  g->n_cells_nonempty = g->h_misc->nonempty;
   return ZB_OK;
 }
 
@@ -828,6 +859,7 @@ void zb_grid_destroy(zb_grid* g) {
     if (sl.released) cudaEventDestroy(sl.released);
     free_buf(sl.buf);
   }
+  if (g->info_event) cudaEventDestroy(g->info_event);
   if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
   if (g->nccl.dl) dlclose(g->nccl.dl);
   if (g->h_red) cudaFreeHost(g->h_red);
@@ -1046,6 +1078,10 @@ int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, 
 
 int zb_grid_info(zb_grid* g, zb_info* out) {
   if (!g || !out) return ZB_ERR_BAD_ARG;
+  if (g->info_pending) {
+    ZB_TRY(enter(g));
+    ZB_TRY(collect_info(g));
+  }
   memset(out, 0, sizeof *out);
   for (int d = 0; d < 3; ++d) {
     out->inf[d] = g->inf[d];
@@ -1060,7 +1096,7 @@ int zb_grid_info(zb_grid* g, zb_info* out) {
   }
   out->cutoff = g->cutoff;
   out->n = g->n;
-  out->n_cells = g->n_cells_nonempty;
+  out->n_cells = g->n_cells_nonempty;  // (collected above when the last rebuild returned without a sync)
   out->ndim = g->ndim;
   out->dtype = g->dtype;
   out->keys_changed = g->keys_changed;
@@ -1125,6 +1161,7 @@ int zb_grid_neighbor_indices(zb_grid* g, int32_t* out, int32_t* count) {
 int zb_grid_cells(zb_grid* g, int32_t* keys, uint32_t* begin, uint32_t* count, uint64_t cap, uint64_t* n_out) {
   ZB_TRY(enter(g));
   ZB_TRY(check_built(g));
+  ZB_TRY(collect_info(g));
   if (!n_out) return fail(g, ZB_ERR_BAD_ARG, "n_out is NULL");
   *n_out = g->n_cells_nonempty;
   if (cap < g->n_cells_nonempty) return fail(g, ZB_ERR_CAPACITY, "need room for %llu cells", (unsigned long long)*n_out);
