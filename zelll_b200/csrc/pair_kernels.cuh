@@ -419,7 +419,11 @@ struct LjConsumer {
     unsigned long long* block_totals;   // [gridDim.x]
   };
   // exact loop: (32 + 32 NJ) dsq values; prefilter loop (f64 only): kQueueSlots packed positions
-  static constexpr int kExactBytes = (32 + 32 * GenericNJ<T>::value * ZB_LJ_FUSE) * (int)sizeof(T);
+#ifndef ZB_LJ_DRAIN_ROWS
+#define ZB_LJ_DRAIN_ROWS 2
+#endif
+  static constexpr int kDrainRows = ZB_LJ_DRAIN_ROWS;
+  static constexpr int kExactBytes = (32 * kDrainRows + 32 * GenericNJ<T>::value * ZB_LJ_FUSE) * (int)sizeof(T);
   static constexpr int kPfBytes = sizeof(T) == 8 ? kQueueSlots * 4 : 0;
   static constexpr int kWarpSmemBytes = kExactBytes > kPfBytes ? kExactBytes : kPfBytes;
   static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
@@ -447,7 +451,20 @@ struct LjConsumer {
     ex.c2 = c2;
   }
   __device__ __forceinline__ uint32_t* q32() { return reinterpret_cast<uint32_t*>(q); }
+  // what the exact loop left in the queue (< kDrainRows rows of dsq values)
+  __device__ __forceinline__ void drain_exact_leftovers() {
+    __syncwarp();
+    for (uint32_t r = 0; r < qn; r += 32) {
+      if (r + lane_id() < qn) {
+        acc += (double)lj_term(q[r + lane_id()]);
+        cnt += 1;
+      }
+    }
+    qn = 0;
+    __syncwarp();
+  }
   __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>* staged, bool prefilter) {
+    if (prefilter && !pf) drain_exact_leftovers();  // the prefilter queue aliases the same bytes
     ex.rec = staged;
     pf = prefilter;
   }
@@ -472,13 +489,18 @@ struct LjConsumer {
       if (h[k]) q[qn + __popc(b & ltmask)] = dsq[k];
       qn += __popc(b);
     }
-    // at most NJ rows can have filled up; one copy of the lj code (the kernel must stay small)
+    // drain two rows at a time: their reciprocal / power chains are independent and overlap.  One
+    // copy of the lj code (the kernel must stay small).
 #pragma unroll 1
-    while (qn >= 32) {
+    while (qn >= kDrainRows * 32) {
       __syncwarp();
-      qn -= 32;
-      acc += (double)lj_term(q[qn + lane_id()]);
-      cnt += 1;
+      qn -= kDrainRows * 32;
+      T e[kDrainRows];
+#pragma unroll
+      for (int r = 0; r < kDrainRows; ++r) e[r] = lj_term(q[qn + 32 * r + lane_id()]);
+#pragma unroll
+      for (int r = 0; r < kDrainRows; ++r) acc += (double)e[r];
+      cnt += kDrainRows;
       __syncwarp();
     }
   }
@@ -502,16 +524,12 @@ struct LjConsumer {
   __device__ __forceinline__ void chunk_end() {}
   template <int CMP>
   __device__ __forceinline__ void tile_end(uint32_t) {
-    // the queue refers to this tile's stage: empty it before the stage is reused
+    // prefilter queue entries refer to this tile's stage: empty it before the stage is reused
+    // (the exact loop queues dsq values, which stay valid: they wait for finish())
     __syncwarp();
-    if (qn > 0) {
+    if (pf && qn > 0) {
       const bool v = lane_id() < qn;
-      if (pf) {
-        drain_pf_row<CMP>(v, v ? q32()[lane_id()] : 0u);
-      } else if (v) {
-        acc += (double)lj_term(q[lane_id()]);
-        cnt += 1;
-      }
+      drain_pf_row<CMP>(v, v ? q32()[lane_id()] : 0u);
       qn = 0;
     }
     __syncthreads();
@@ -519,6 +537,7 @@ struct LjConsumer {
   __device__ __forceinline__ void finish() {
     __shared__ double s_e[kPairWarps];
     __shared__ unsigned long long s_c[kPairWarps];
+    if (!pf) drain_exact_leftovers();
     const double w = warp_reduce(acc, [](double x, double y) { return x + y; });
     const unsigned long long c = warp_reduce(cnt, [](unsigned long long x, unsigned long long y) { return x + y; });
     if (lane_id() == 0) {
