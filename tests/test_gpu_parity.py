@@ -605,3 +605,29 @@ def test_prefetch_double_buffering(zb):
     cg.rebuild(frames[1].numpy())  # a different array than the prefetched one: copied normally
     e, m = cg.lj_energy(10.0, "lt", return_pairs=True)
     assert m == want[1][2]
+
+
+def test_full_size_properties_f32(zb):
+    """n = 10^7 in f32 (configs[1]): |z| reaches 5.5e5 where an f32 ulp is 0.06, so coordinates are
+    coarsely quantised and coincident particles occur -- counts and pair sets must still be exact."""
+    n = 10_000_000
+    pts = workload.generate_points_random(n, dtype=np.float32)
+    cg = zb.CellGrid(pts, 10.0, dtype=np.float32)
+    keys, begin, count = cg.cells()
+    assert int(count.sum()) == n and np.all(np.diff(keys) > 0)
+    c_le, c_lt = cg.pair_count(10.0, "le"), cg.pair_count(10.0, "lt")
+    e, m = cg.lj_energy(10.0, "lt", return_pairs=True)
+    assert m == c_lt <= c_le <= cg.pair_count()
+    assert 15.5 * n < c_lt < 16.5 * n
+    # the 150k particles of largest |z| (coarsest quantisation) form a closed sub-box: bit-exact pair set
+    order = np.argsort(pts[:, 2], kind="stable")
+    sub = np.ascontiguousarray(pts[order[:150_000]])
+    og = OracleCellGrid(sub, 10.0, dtype=np.float32)
+    cs = zb.CellGrid(sub, 10.0, dtype=np.float32)
+    assert np.array_equal(cs.keys(), og.keys())
+    for cmp in ("lt", "le"):
+        assert np.array_equal(canonical_pairs(cs.particle_pairs(10.0, cmp)), og.pairs_canonical(OCMP[cmp], 10.0))
+    # permutation invariance of the counts
+    perm = np.random.default_rng(1).permutation(n)
+    cg.rebuild(pts[perm])
+    assert cg.pair_count(10.0, "lt") == c_lt and cg.pair_count(10.0, "le") == c_le
