@@ -122,3 +122,35 @@ def test_workload_generators_and_lammps_writer():
     assert text[2] == "3 atoms" and text[3] == "1 atom types"
     assert text[4] == "-15 15 xlo xhi" and text[8] == "Atoms # atomic"
     assert text[10].split()[:2] == ["1", "1"] and float(text[10].split()[2]) == pts[0, 0]
+
+
+def test_header_is_valid_c_and_links(tmp_path, lib):
+    """include/zelll_b200.h must compile as plain C (the boundary a cgo / Rust-sys / ctypes binding sees) and a
+    C program must link against the library and get a clean error without a GPU (or a grid with one)."""
+    import subprocess
+
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(
+        '#include "zelll_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  zb_grid* g = 0;\n"
+        "  int rc = zb_grid_create(ZB_F64, 3, 0, &g);\n"
+        '  printf("abi %d rc %d\\n", zb_abi_version(), rc);\n'
+        "  if (rc == ZB_OK) {\n"
+        "    double xyz[6] = {0, 0, 0, 0.5, 0.5, 0.5}, c = 1.0, e; unsigned long long m; uint64_t mm;\n"
+        "    rc = zb_grid_rebuild(g, xyz, 2, &c);\n"
+        "    if (rc == ZB_OK) rc = zb_grid_lj_energy(g, ZB_CMP_LT, c, &e, &mm);\n"
+        "    m = mm; printf(\"pairs %llu rc %d\\n\", m, rc);\n"
+        "    zb_grid_destroy(g);\n"
+        "  }\n"
+        "  return (rc == ZB_OK || rc == ZB_ERR_CUDA) ? 0 : 1;\n"
+        "}\n"
+    )
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.join(ROOT, "zelll_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lzelll_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi 1" in out.stdout
