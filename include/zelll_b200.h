@@ -84,6 +84,11 @@ int zb_grid_set_stream(zb_grid* g, void* cuda_stream);
  * FlatIndex::rebuild_mut returns (flatindex.rs:113-153).  Off by default (costs one extra pass). */
 int zb_grid_track_key_changes(zb_grid* g, int enable);
 
+/* Stable cell storage: later rebuilds keep the particles of a cell in label (= input) order, as
+ * CellStorage::push does (src/cellgrid/storage.rs:77-81), at the cost of one extra pass; it also
+ * makes pair order inside a cell and the energy's summation order reproducible.  Off by default. */
+int zb_grid_set_stable(zb_grid* g, int enable);
+
 const char* zb_last_error(const zb_grid* g);
 
 /* -- construction -------------------------------------------------------------------------- */

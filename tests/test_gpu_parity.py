@@ -631,3 +631,28 @@ def test_full_size_properties_f32(zb):
     perm = np.random.default_rng(1).permutation(n)
     cg.rebuild(pts[perm])
     assert cg.pair_count(10.0, "lt") == c_lt and cg.pair_count(10.0, "le") == c_le
+
+
+def test_stable_cell_storage_matches_reference_order(zb):
+    """With zb_grid_set_stable the records of every cell are in input order, exactly the slices the
+    reference's stable push produces (storage.rs:77-81); the pair set is unchanged."""
+    for kind, n in (("lj", 20000), ("dense", 3000), ("cube", 4000)):
+        pts, cutoff = _cloud(kind, n, np.float64)
+        cg = zb.CellGrid(pts, cutoff)
+        cg.set_stable(True)
+        cg.rebuild(pts)
+        og = OracleCellGrid(pts, cutoff)
+        keys, begin, count = cg.cells()
+        labels, xyz = cg.cell_storage()
+        okeys, obegin, olen = og.cells()
+        olabels, _ = og.cell_storage()
+        oslot = {int(k): i for i, k in enumerate(okeys)}
+        for k, b, c in zip(keys, begin, count):
+            ob, oc = int(obegin[oslot[int(k)]]), int(olen[oslot[int(k)]])
+            assert labels[b:b + c].tolist() == olabels[ob:ob + oc].tolist()
+        assert np.array_equal(canonical_pairs(cg.particle_pairs(cutoff, "le")), og.pairs_canonical(CMP_LE, cutoff))
+        e1 = cg.lj_energy(cutoff, "lt")
+        cg.rebuild(pts)
+        assert np.array_equal(cg.cell_storage()[0], labels)   # reproducible layout
+        _, e64, _ = og.lj_energy(CMP_LT, cutoff)
+        assert abs(e1 - e64) <= F64_RTOL * abs(e64)

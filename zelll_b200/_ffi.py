@@ -59,6 +59,7 @@ SIGNATURES = {
     "zb_grid_destroy": (None, [_vp]),
     "zb_grid_set_stream": (_int, [_vp, _vp]),
     "zb_grid_track_key_changes": (_int, [_vp, _int]),
+    "zb_grid_set_stable": (_int, [_vp, _int]),
     "zb_last_error": (C.c_char_p, [_vp]),
     "zb_grid_rebuild": (_int, [_vp, _vp, _u64, _dp]),
     "zb_grid_prefetch": (_int, [_vp, _vp, _u64]),

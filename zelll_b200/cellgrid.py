@@ -326,6 +326,10 @@ class CellGrid:
         """`CellGrid::rebuild_mut(&mut self, particles, Option<T>)` (cellgrid.rs:264-312)."""
         self.rebuild(particles, cutoff)
 
+    def set_stable(self, enable: bool = True) -> None:
+        """Keep the particles of a cell in input order from the next rebuild on (storage.rs:77-81)."""
+        self._check(self._lib.zb_grid_set_stable(self._h, int(enable)))
+
     def track_key_changes(self, enable: bool = True) -> None:
         self._check(self._lib.zb_grid_track_key_changes(self._h, int(enable)))
 

@@ -390,6 +390,56 @@ __global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Optional stable order (zb_grid_set_stable): K4 ranks the particles of a cell by atomic arrival,
+// the reference's CellStorage::push keeps input order (storage.rs:77-81).  One thread per cell
+// sorts its records by label in place (heap sort: O(m log m), no extra memory); with labels =
+// enumerate order this reproduces the reference's within-cell order and makes cell_storage(), the
+// pair list order inside a cell and the floating-point summation order run-to-run reproducible.
+template <class T>
+__device__ __forceinline__ void sift_down(Rec<T>* a, uint32_t start, uint32_t end) {
+  uint32_t root = start;
+  while (2 * root + 1 < end) {
+    uint32_t child = 2 * root + 1;
+    if (child + 1 < end && load_rec(a + child).label < load_rec(a + child + 1).label) ++child;
+    const Rec<T> r = load_rec(a + root), c = load_rec(a + child);
+    if (r.label >= c.label) return;
+    store_rec(a + root, c.x, c.y, c.z, c.label);
+    store_rec(a + child, r.x, r.y, r.z, r.label);
+    root = child;
+  }
+}
+
+template <class T>
+__global__ void cell_sort_kernel(const uint32_t* __restrict__ csr, uint32_t ncells, Rec<T>* __restrict__ sorted) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const uint32_t b = csr[c], m = csr[c + 1] - b;
+  if (m < 2) return;
+  Rec<T>* a = sorted + b;
+  if (m <= 16) {  // insertion sort: the common case (~10 particles per cell)
+    for (uint32_t i = 1; i < m; ++i) {
+      const Rec<T> key = load_rec(a + i);
+      uint32_t j = i;
+      while (j > 0) {
+        const Rec<T> p = load_rec(a + j - 1);
+        if (p.label <= key.label) break;
+        store_rec(a + j, p.x, p.y, p.z, p.label);
+        --j;
+      }
+      store_rec(a + j, key.x, key.y, key.z, key.label);
+    }
+    return;
+  }
+  for (uint32_t start = m / 2; start-- > 0;) sift_down(a, start, m);
+  for (uint32_t end = m - 1; end > 0; --end) {
+    const Rec<T> top = load_rec(a), last = load_rec(a + end);
+    store_rec(a, last.x, last.y, last.z, last.label);
+    store_rec(a + end, top.x, top.y, top.z, top.label);
+    sift_down(a, 0u, end);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // inspection helpers
 
 // FlatIndex.index in input order, recomputed from the cell-sorted records (same arithmetic as K2)

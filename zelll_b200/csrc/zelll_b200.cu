@@ -90,6 +90,7 @@ struct zb_grid {
   uint32_t home_lo = 0, home_hi = 1;
   bool sharded = false;
   bool track_keys = false;
+  bool stable = false;  // zb_grid_set_stable: records of a cell in label (= input) order
   bool slab_check_pending = false;  // an asynchronous zb_slab_top_layer awaits its verdict
   int keys_changed = -1;
   uint64_t n_keys_old = 0;
@@ -391,6 +392,11 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n) {
       scatter_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
     else
       scatter_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
+    g->launches++;
+  }
+  if (g->stable && n > 1) {
+    cell_sort_kernel<T><<<(uint32_t)((nc + 127) / 128), 128, 0, g->stream>>>(csr_ptr(g), (uint32_t)nc,
+                                                                            static_cast<Rec<T>*>(g->sorted.p));
     g->launches++;
   }
   ZB_CUDA(cudaGetLastError());
@@ -881,6 +887,12 @@ int zb_grid_set_stream(zb_grid* g, void* cuda_stream) {
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   g->stream = static_cast<cudaStream_t>(cuda_stream);
   g->own_stream = false;
+  return ZB_OK;
+}
+
+int zb_grid_set_stable(zb_grid* g, int enable) {
+  if (!g) return ZB_ERR_BAD_ARG;
+  g->stable = enable != 0;
   return ZB_OK;
 }
 
