@@ -122,6 +122,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   }
 }
 
+// shared-memory access by 32-bit shared-space address (the hit queues of the consumers)
+__device__ __forceinline__ void st_shared(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
+}
+__device__ __forceinline__ void st_shared(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v));
+}
+// a * b + c as ONE opaque instruction (keeps the compiler from re-associating the running queue
+// address into separate index sums)
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+template <class T>
+__device__ __forceinline__ T ld_shared(uint32_t a);
+template <>
+__device__ __forceinline__ double ld_shared<double>(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+template <>
+__device__ __forceinline__ float ld_shared<float>(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
 // lj (benches/lj.rs:42-47): dsq.recip().powi(3) -> (r*r)*r ; 4*t*(t-1).  Exact IEEE division.
 template <class T>
 __device__ __forceinline__ T lj_term(T dsq) {
@@ -439,14 +468,17 @@ struct LjConsumer {
   Args a;
   ExactCtx<T> ex;
   T* q;          // exact loop: dsq; prefilter loop: uint32 (ipos << 16 | jpos) in the same bytes
-  uint32_t qn;   // warp-uniform fill level
+  uint32_t qn;   // prefilter loop: warp-uniform fill level (entries)
+  uint32_t q0;   // exact loop: shared-space byte address of q ...
+  uint32_t qa;   // ... and of its fill position (warp-uniform)
   bool pf;
   unsigned ltmask;
   double acc;
   unsigned long long cnt;  // per-lane pairs kept
 
   __device__ LjConsumer(const Args& args, ConsumerSmem*, void* warp_smem, T c2)
-      : a(args), q(static_cast<T*>(warp_smem)), qn(0), pf(false), ltmask(lanemask_lt()), acc(0.0), cnt(0) {
+      : a(args), q(static_cast<T*>(warp_smem)), qn(0), q0(smem_u32(warp_smem)), qa(q0), pf(false),
+        ltmask(lanemask_lt()), acc(0.0), cnt(0) {
     ex.rec = nullptr;
     ex.c2 = c2;
   }
@@ -454,13 +486,14 @@ struct LjConsumer {
   // what the exact loop left in the queue (< kDrainRows rows of dsq values)
   __device__ __forceinline__ void drain_exact_leftovers() {
     __syncwarp();
-    for (uint32_t r = 0; r < qn; r += 32) {
-      if (r + lane_id() < qn) {
-        acc += (double)lj_term(q[r + lane_id()]);
+    const uint32_t left = (qa - q0) / (uint32_t)sizeof(T);
+    for (uint32_t r = 0; r < left; r += 32) {
+      if (r + lane_id() < left) {
+        acc += (double)lj_term(ld_shared<T>(q0 + (r + lane_id()) * (uint32_t)sizeof(T)));
         cnt += 1;
       }
     }
-    qn = 0;
+    qa = q0;
     __syncwarp();
   }
   __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>* staged, bool prefilter) {
@@ -483,21 +516,25 @@ struct LjConsumer {
   template <int NJ>
   __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&dsq)[NJ], const uint32_t (&)[NJ],
                                          const uint32_t (&)[NJ]) {
+    // the fill position is kept as a shared-space BYTE address: slot address = one multiply-add,
+    // advancing it = one multiply-add (an element index costs an extra add per test)
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
       const unsigned b = __ballot_sync(0xffffffffu, h[k]);
-      if (h[k]) q[qn + __popc(b & ltmask)] = dsq[k];
-      qn += __popc(b);
+      if (h[k]) st_shared(mad_u32(__popc(b & ltmask), sizeof(T), qa), dsq[k]);
+      qa = mad_u32(__popc(b), sizeof(T), qa);
     }
     // drain two rows at a time: their reciprocal / power chains are independent and overlap.  One
     // copy of the lj code (the kernel must stay small).
+    constexpr uint32_t kRowsBytes = kDrainRows * 32 * sizeof(T);
 #pragma unroll 1
-    while (qn >= kDrainRows * 32) {
+    while (qa >= q0 + kRowsBytes) {
       __syncwarp();
-      qn -= kDrainRows * 32;
+      qa -= kRowsBytes;
       T e[kDrainRows];
 #pragma unroll
-      for (int r = 0; r < kDrainRows; ++r) e[r] = lj_term(q[qn + 32 * r + lane_id()]);
+      for (int r = 0; r < kDrainRows; ++r)
+        e[r] = lj_term(ld_shared<T>(qa + (32 * r + lane_id()) * (uint32_t)sizeof(T)));
 #pragma unroll
       for (int r = 0; r < kDrainRows; ++r) acc += (double)e[r];
       cnt += kDrainRows;
