@@ -209,6 +209,51 @@ __device__ __forceinline__ void load_part(const Rec<double>* p, double& x, doubl
   }
 }
 
+// Where the exact loop reads records from.  at(pos) rebases, load(pos) reads record `pos`.
+//  * GlobalRecs: the cell-sorted array in global memory (tiles too large for the stage);
+//  * StagedRecs: the shared-memory stage, addressed by a 32-bit shared-space BYTE address that is
+//    biased by the stage's first record (wraps mod 2^32).  Explicit ld.shared keeps the address in
+//    ONE register; through a generic pointer the compiler re-derived the shared window base
+//    (S2UR SR_CgaCtaId + 3 uniform instructions) inside every test-loop iteration.
+template <class T>
+struct GlobalRecs {
+  const Rec<T>* p;
+  __device__ __forceinline__ GlobalRecs at(uint32_t pos) const { return GlobalRecs{p + pos}; }
+  template <bool LABEL>
+  __device__ __forceinline__ void load(uint32_t pos, T& x, T& y, T& z, uint32_t& label) const {
+    load_part<LABEL>(p + pos, x, y, z, label);
+  }
+};
+template <bool LABEL>
+__device__ __forceinline__ void ld_shared_part(uint32_t a, float& x, float& y, float& z, uint32_t& label) {
+  float w;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+  label = LABEL ? __float_as_uint(w) : 0u;
+}
+template <bool LABEL>
+__device__ __forceinline__ void ld_shared_part(uint32_t a, double& x, double& y, double& z, uint32_t& label) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+  if (LABEL) {
+    double w;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(z), "=d"(w) : "r"(a));
+    label = (uint32_t)__double2loint(w);
+  } else {
+    asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(a));
+    label = 0u;
+  }
+}
+template <class T>
+struct StagedRecs {
+  uint32_t a;
+  __device__ __forceinline__ StagedRecs at(uint32_t pos) const {
+    return StagedRecs{a + pos * (uint32_t)sizeof(Rec<T>)};
+  }
+  template <bool LABEL>
+  __device__ __forceinline__ void load(uint32_t pos, T& x, T& y, T& z, uint32_t& label) const {
+    ld_shared_part<LABEL>(a + pos * (uint32_t)sizeof(Rec<T>), x, y, z, label);
+  }
+};
+
 // the reference's distance_squared between two records, optionally with their labels
 template <class T, bool LABEL>
 __device__ __forceinline__ T exact_dsq(const Rec<T>* a, const Rec<T>* b, uint32_t& la, uint32_t& lb) {
@@ -646,7 +691,7 @@ __device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, co
 
 // ---------------------------------------------------------------------------------------------
 // Exact loop: one warp enumerates the half-shell pairs of home cell c in the arithmetic of T.
-//   recb / csrb are biased base pointers: recb[pos] is record `pos` of the cell-sorted array and
+//   recb / csrb are biased bases (GlobalRecs / StagedRecs): recb.load(pos) is record `pos` of the cell-sorted array and
 //   csrb[cell] its CSR entry, whether they live in shared memory (staged tile) or in global memory.
 //   Every lane keeps NJ candidates j in registers; the home particles i are broadcast loads.
 // P > 1 is the packed tail: the chunk has at most 32 / P candidates, the warp is split into P
@@ -654,15 +699,15 @@ __device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, co
 // ceil(m / P) times instead of m.  A phase whose particle index runs past the cell reads a
 // neighbouring record (in bounds: the stage and the record array have slack) and discards it
 // through i < thr <= m.
-template <class T, int CMP, int NJ, int P, class Consumer>
-__device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uint32_t m, uint32_t ph,
+template <class T, int CMP, int NJ, int P, class Recs, class Consumer>
+__device__ __forceinline__ void exact_tests(const Recs home, uint32_t m, uint32_t ph,
                                             const T (&xj)[NJ], const T (&yj)[NJ], const T (&zj)[NJ],
                                             const uint32_t (&lj)[NJ], const uint32_t (&thr)[NJ], T c2,
                                             Consumer& cons) {
   constexpr int F = Consumer::kFuse;  // home particles per consumer call
   auto test = [&](uint32_t i, bool* h, T* dsq, uint32_t& li) {
     T xi, yi, zi;
-    load_part<Consumer::kNeedLabels>(home + i, xi, yi, zi, li);
+    home.template load<Consumer::kNeedLabels>(i, xi, yi, zi, li);
 #pragma unroll
     for (int q = 0; q < NJ; ++q) {
       h[q] = i < thr[q];
@@ -700,8 +745,8 @@ __device__ __forceinline__ void exact_tests(const Rec<T>* __restrict__ home, uin
 
 // one group of up to 32 NJ candidates (lane l holds candidates kb + 32 q + l), or -- P > 1 -- a
 // packed tail of up to 32 / P candidates (lane l holds candidate kb + l % (32 / P))
-template <class T, int CMP, int NJ, int P, class Consumer>
-__device__ __forceinline__ void process_group(const CellRuns& r, const Rec<T>* __restrict__ recb, uint32_t kb, T c2,
+template <class T, int CMP, int NJ, int P, class Recs, class Consumer>
+__device__ __forceinline__ void process_group(const CellRuns& r, const Recs recb, uint32_t kb, T c2,
                                               Consumer& cons) {
   constexpr uint32_t W = 32 / P;
   const unsigned lane = lane_id();
@@ -712,14 +757,14 @@ __device__ __forceinline__ void process_group(const CellRuns& r, const Rec<T>* _
   for (int q = 0; q < NJ; ++q) {
     const uint32_t k = kb + 32u * q + slot;
     thr[q] = r.thr(k);
-    load_part<Consumer::kNeedLabels>(recb + r.pos(k), xj[q], yj[q], zj[q], lj[q]);
+    recb.template load<Consumer::kNeedLabels>(r.pos(k), xj[q], yj[q], zj[q], lj[q]);
   }
-  exact_tests<T, CMP, NJ, P>(recb + r.hb, r.m, ph, xj, yj, zj, lj, thr, c2, cons);
+  exact_tests<T, CMP, NJ, P>(recb.at(r.hb), r.m, ph, xj, yj, zj, lj, thr, c2, cons);
   cons.chunk_end();
 }
 
-template <class T, int CMP, class Consumer>
-__device__ __forceinline__ void process_cell(const CellRuns& r, const Rec<T>* __restrict__ recb, T c2, Consumer& cons) {
+template <class T, int CMP, class Recs, class Consumer>
+__device__ __forceinline__ void process_cell(const CellRuns& r, const Recs recb, T c2, Consumer& cons) {
   constexpr int NJMAX = GenericNJ<T>::value;
   if (r.m == 0) return;
   if (CMP == 0 && Consumer::kCountsOnly) {  // unfiltered count: no per-pair work
@@ -902,17 +947,20 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
       }
     }
     __syncthreads();
+    // the stage as a biased shared-space address, pinned in a register for the whole tile
+    StagedRecs<T> srecs{smem_u32(s_rec) - plo * (uint32_t)sizeof(Rec<T>)};
+    asm volatile("" : "+r"(srecs.a));
     // warps claim home cells one at a time: the first kPairWarps statically, the rest from s_next
     for (uint32_t c = c0 + warp; c < c1;) {
       const CellRuns r = s_desc[c - c0];
       // separate call sites so that the staged ones compile to shared-memory loads (LDS)
       if constexpr (kCanPrefilter) {
         if (pf) process_cell_prefilter<CMP>(r, s_rel, plo, lo, hi, cons);
-        else if (staged) process_cell<T, CMP>(r, s_rec - plo, c2, cons);
-        else process_cell<T, CMP>(r, p.sorted, c2, cons);
+        else if (staged) process_cell<T, CMP>(r, srecs, c2, cons);
+        else process_cell<T, CMP>(r, GlobalRecs<T>{p.sorted}, c2, cons);
       } else {
-        if (staged) process_cell<T, CMP>(r, s_rec - plo, c2, cons);
-        else process_cell<T, CMP>(r, p.sorted, c2, cons);
+        if (staged) process_cell<T, CMP>(r, srecs, c2, cons);
+        else process_cell<T, CMP>(r, GlobalRecs<T>{p.sorted}, c2, cons);
       }
       uint32_t nxt = 0;
       if (lane == 0) nxt = atomicAdd(&s_next, 1u);
