@@ -330,8 +330,10 @@ struct CountConsumer {
   template <int NJ>
   __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], const uint32_t (&)[NJ],
                                          const uint32_t (&)[NJ]) {
+    // one predicated add per test (plain C++ compiles to an add plus a predicated move)
 #pragma unroll
-    for (int q = 0; q < NJ; ++q) c32 += h[q] ? 1u : 0u;
+    for (int q = 0; q < NJ; ++q)
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c32) : "r"((uint32_t)h[q]));
   }
   // prefilter: sure hits are counted at once; the rare in-band pair is decided in f64 on the spot
   template <int CMP, int NJ>
