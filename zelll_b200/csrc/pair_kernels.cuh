@@ -87,6 +87,8 @@ struct PairParams {
   FastDiv div0, div1;   // division by w0 and by w1
   const uint32_t* tile_list;   // sparse boxes: ids of the tiles that hold home particles, else nullptr
   const uint32_t* tile_list_n; // ... and their number (device memory)
+  uint32_t* tile_next;         // dynamic tile claim: work items handed out beyond the first wave; 0 between launches
+  uint32_t* tile_done;         // CTAs that finished; the last one out re-arms both counters
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -868,6 +870,7 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ ConsumerSmem s_cs;
   __shared__ uint32_t s_next;  // next unclaimed home cell of the tile (dynamic balance between warps)
+  __shared__ uint32_t s_tile[2];  // this CTA's next work item (claimed one tile ahead)
 
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
@@ -881,7 +884,14 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
   const uint32_t plane = (uint32_t)p.w0 * (uint32_t)p.w1;
   const uint32_t halo = plane + (uint32_t)p.w0 + 1u;
   const uint32_t nwork = p.tile_list ? __ldg(p.tile_list_n) : p.ntiles;
-  for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+  // Work items are claimed DYNAMICALLY: the first wave statically (blockIdx.x), every further one
+  // from a global counter, so that CTAs which drew cheap tiles take more of them (clustered
+  // particle distributions; also the last, partial wave of a uniform box).  The claim is issued
+  // at the start of a tile and read at its end, its round trip hides behind the tile's work;
+  // s_tile is double-buffered so that the next claim cannot overwrite a value still being read.
+  uint32_t par = 0;
+  for (uint32_t w = blockIdx.x; w < nwork;) {
+    if (threadIdx.x == 0) s_tile[par] = gridDim.x + atomicAdd(p.tile_next, 1u);
     const uint32_t tile = p.tile_list ? __ldg(p.tile_list + w) : w;
     const uint32_t c0 = p.home_lo + tile * p.tile_cells;
     const uint32_t c1 = min(c0 + p.tile_cells, p.home_hi);
@@ -890,7 +900,12 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
     const uint32_t plo = __ldg(p.csr + cl), phi = __ldg(p.csr + c1);
     const uint32_t np = phi - plo;
     // sparse boxes: a tile without home particles has no pairs (its per-tile count stays 0)
-    if (phi == __ldg(p.csr + c0)) continue;
+    if (phi == __ldg(p.csr + c0)) {
+      __syncthreads();
+      w = s_tile[par];
+      par ^= 1u;
+      continue;
+    }
     const bool staged = np <= p.stage_recs && ncsr <= (uint32_t)kStageCells;
 
     // prefilter thresholds of this tile (warp-uniform)
@@ -969,8 +984,16 @@ __global__ void __launch_bounds__(kPairThreads, ZB_PAIR_MINBLOCKS) pair_kernel(P
       c = __shfl_sync(0xffffffffu, nxt, 0);
     }
     cons.template tile_end<CMP>(w);  // ends with __syncthreads(): the stage buffers may be overwritten
+    w = s_tile[par];
+    par ^= 1u;
   }
   cons.finish();
+  // every claim of this CTA precedes its `done` tick, so the CTA that sees the last tick knows that
+  // nobody will touch tile_next again (atomicInc wraps tile_done back to 0 by itself)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(p.tile_done, gridDim.x - 1) == gridDim.x - 1) *p.tile_next = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -50,7 +50,9 @@ struct Misc {
   uint32_t nonempty;       // scan: non-empty cells
   int flags;               // count: bit0 = particle outside the window
   int keys_changed;        // keys_changed_kernel
-  int pad[3];
+  uint32_t pair_next;      // pair kernels: dynamic tile claim (self re-arming, 0 between launches)
+  uint32_t pair_done;      // pair kernels: CTAs finished
+  int pad;
   double out6[6];          // bbox result (T-typed, stored in the leading bytes)
   double energy;           // finalize_kernel
   unsigned long long pair_total;
@@ -652,6 +654,8 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.prefilter = pl.prefilter ? 1 : 0;
   p.tile_list = nullptr;
   p.tile_list_n = nullptr;
+  p.tile_next = &g->misc->pair_next;
+  p.tile_done = &g->misc->pair_done;
   p.div0 = make_fastdiv((uint32_t)g->wshape[0]);
   p.div1 = make_fastdiv((uint32_t)g->wshape[1]);
   return p;
