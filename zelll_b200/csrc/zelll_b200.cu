@@ -614,6 +614,10 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   // enough tiles to balance the persistent grid
   const uint32_t want_tiles = (uint32_t)g->sm_count * 4 * 4;
   if (nhome / std::max(tc, 1u) < want_tiles) tc = std::max<uint32_t>(8, (nhome + want_tiles - 1) / want_tiles);
+  if (const char* e = getenv("ZB_TILE_CELLS")) {     // tuning knob for experiments
+    const long v = atol(e);
+    if (v >= 1) tc = (uint32_t)v;
+  }
   tc = std::min<uint32_t>(std::max<uint32_t>(tc, 1), kMaxTileCells);
   pl.tile_cells = tc;
   pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
