@@ -60,9 +60,11 @@ __device__ __forceinline__ void store_rec(Rec<float>* p, float x, float y, float
   *reinterpret_cast<float4*>(p) = make_float4(x, y, z, __uint_as_float(label));
 }
 __device__ __forceinline__ void store_rec(Rec<double>* p, double x, double y, double z, uint32_t label) {
-  double2* q = reinterpret_cast<double2*>(p);
-  q[0] = make_double2(x, y);
-  q[1] = make_double2(z, __longlong_as_double((long long)label));
+  // ONE 256-bit store (sm_100 STG.256): the record is one aligned 32-byte sector, written whole
+  // instead of as two half-sector requests that the L2 has to merge
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z),
+               "d"(__longlong_as_double((long long)label))
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
