@@ -186,7 +186,9 @@ def slab_points(torch, rank: int, world: int, n_per: int, device, spare: int):
     if rank == 0:
         buf[0] = torch.tensor([-15.0, -15.0, -L / 2.0], dtype=torch.float64)
     if rank == world - 1:
-        buf[n_per - 1] = torch.tensor([15.0, 15.0, -L / 2.0 + CUTOFF * (nz - 1) + 0.5 * (L - CUTOFF * (nz - 1))],
+        # just inside the open upper faces: uniform draws never reach +15, the grid stays 3 x 3 x nz cells
+        # like the single-GPU box (a corner AT +15 would open a fourth, empty cell column in x and y)
+        buf[n_per - 1] = torch.tensor([15.0 - 1e-9, 15.0 - 1e-9, -L / 2.0 + CUTOFF * (nz - 1) + 0.5 * (L - CUTOFF * (nz - 1))],
                                       dtype=torch.float64)
     del u
     return buf

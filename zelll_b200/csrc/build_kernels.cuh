@@ -204,21 +204,64 @@ constexpr int kPointThreads = 256;
 // issued before the first atomic, which keeps kPointIlp L2 round trips in flight per thread.
 constexpr int kPointIlp = 1;  // measured: 4 is ~10 % slower (the kernels are bound by random sector traffic, not latency)
 
-template <class T, int NDIM>
+// particle labels travel through f32 / f64 halo rows as raw bits
+template <class T>
+__device__ __forceinline__ T label_bits(uint32_t label);
+template <>
+__device__ __forceinline__ float label_bits<float>(uint32_t label) { return __uint_as_float(label); }
+template <>
+__device__ __forceinline__ double label_bits<double>(uint32_t label) { return __longlong_as_double((long long)label); }
+__device__ __forceinline__ uint32_t label_from_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t label_from_bits(double v) { return (uint32_t)__double_as_longlong(v); }
+
+// Slab-local multi-GPU step: while counting its own rows a rank also picks out the particles of its
+// TOP layer -- the lower halo of the next rank -- as rows {x, y, z, label} of out[1..] (order
+// unspecified; their number accumulates in *count), so the halo costs no extra pass over the input.
+// A row outside the rank's own layers [first, top] of the slab axis sets *bad.
+template <class T>
+struct TopLayerOut {
+  T* out;
+  uint32_t cap;
+  uint32_t* count;
+  int* bad;
+  uint32_t label_offset;
+  int first, top;  // window-relative layers of z_begin and z_end - 1
+};
+
+template <class T, int NDIM, bool TOP>
 __global__ void __launch_bounds__(kPointThreads) count_kernel(const T* __restrict__ xyz, uint32_t n,
                                                               GridParams<T> g,
                                                               uint32_t* __restrict__ counts,
-                                                              int* __restrict__ flags) {
+                                                              int* __restrict__ flags, TopLayerOut<T> tl) {
   const uint32_t base = blockIdx.x * (kPointThreads * kPointIlp) + threadIdx.x;
   uint32_t c[kPointIlp];
 #pragma unroll
   for (int k = 0; k < kPointIlp; ++k) {
     const uint32_t i = base + k * kPointThreads;
     c[k] = 0xfffffffeu;  // beyond n
+    T x = T(0), y = T(0), z = T(0);
+    bool top = false;
     if (i < n) {
-      T x, y, z;
       load_point<T, NDIM>(xyz, i, x, y, z);
       c[k] = local_cell(g, x, y, z);
+      if (TOP) {
+        const int layer = cell_coord(NDIM == 3 ? z : y, g.inf[NDIM - 1], g.cutoff) - g.wlo[NDIM - 1];
+        if (layer < tl.first || layer > tl.top) *tl.bad = 1;
+        top = layer == tl.top;
+      }
+    }
+    if (TOP) {  // warp-aggregated append (every thread of the warp gets here)
+      const unsigned b = __ballot_sync(0xffffffffu, top);
+      if (b != 0) {
+        uint32_t slot0 = 0;
+        if (lane_id() == 0) slot0 = atomicAdd(tl.count, (uint32_t)__popc(b));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        const uint32_t slot = slot0 + __popc(b & lanemask_lt());
+        if (top && slot < tl.cap) {
+          T* row = tl.out + (uint64_t)(slot + 1) * 4;
+          row[0] = x; row[1] = y; row[2] = z; row[3] = label_bits<T>(tl.label_offset + i);
+        }
+      }
     }
   }
 #pragma unroll
@@ -462,16 +505,6 @@ __global__ void keys_changed_kernel(const int32_t* __restrict__ old_keys, uint32
   int32_t o = i < n_old ? old_keys[i] : 0;
   if (o != new_keys[i]) *changed = 1;
 }
-
-// particle labels travel through f32 / f64 halo rows as raw bits
-template <class T>
-__device__ __forceinline__ T label_bits(uint32_t label);
-template <>
-__device__ __forceinline__ float label_bits<float>(uint32_t label) { return __uint_as_float(label); }
-template <>
-__device__ __forceinline__ double label_bits<double>(uint32_t label) { return __longlong_as_double((long long)label); }
-__device__ __forceinline__ uint32_t label_from_bits(float v) { return __float_as_uint(v); }
-__device__ __forceinline__ uint32_t label_from_bits(double v) { return (uint32_t)__double_as_longlong(v); }
 
 // bbox result (T) -> 6 doubles in device memory, for all-reducing the box without a host round trip
 template <class T>

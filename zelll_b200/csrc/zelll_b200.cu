@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -336,8 +337,18 @@ int derive_shape(zb_grid* g) {
 // ---------------------------------------------------------------------------------------------
 // K2..K4 launches: counting sort of `xyz` (device) into g->sorted / g->table
 
+// Slab-local multi-GPU step: the count pass over a rank's own rows also extracts its top layer
+// (TopLayerOut); `exchange` then trades halos with the neighbours, appends the received rows behind
+// the local ones and returns their number -- they are counted by a second, tiny launch.
 template <class T>
-int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n) {
+struct SlabHook {
+  TopLayerOut<T> top;
+  uint64_t n_cap;                              // upper bound of local + halo rows (buffer sizing)
+  std::function<int(uint64_t* n_halo)> exchange;
+};
+
+template <class T>
+int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t& n, SlabHook<T>* hook = nullptr) {
   // window -> stored cell count
   uint64_t nc = 1;
   for (int d = 0; d < 3; ++d) {
@@ -359,7 +370,7 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n) {
   ZB_TRY(reserve(g, g->table, table_elems * 4));
   // + 16 records of slack: the packed / fused test loops of the pair kernels may read (and discard) up to 15 records
   // past a home cell
-  ZB_TRY(reserve(g, g->sorted, ((size_t)n + 16) * sizeof(Rec<T>)));
+  ZB_TRY(reserve(g, g->sorted, ((size_t)(hook ? hook->n_cap : n) + 16) * sizeof(Rec<T>)));
   const uint32_t ntile = (uint32_t)((nc + kScanTile - 1) / kScanTile);
   ZB_TRY(reserve(g, g->scan_state, (size_t)ntile * sizeof(unsigned long long)));
 
@@ -370,14 +381,26 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n) {
 
   const GridParams<T> p = make_params<T>(g);
   uint32_t* cursor = cursor_ptr(g);
-  if (n > 0) {
-    StageSpan span(g, ZB_STAGE_COUNT);
-    const uint32_t blocks = (uint32_t)((n + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
-    if (g->ndim == 3)
-      count_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
-    else
-      count_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, (uint32_t)n, p, cursor, &g->misc->flags);
+  auto count = [&](const T* rows, uint64_t m, const TopLayerOut<T>* top) {
+    if (m == 0) return;
+    StageSpan span(g, rows == xyz ? ZB_STAGE_COUNT : ZB_STAGE_OTHER);  // the halo rows' launch is not "the" K2
+    const uint32_t blocks = (uint32_t)((m + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
+    const TopLayerOut<T> tl = top ? *top : TopLayerOut<T>{};
+    if (g->ndim == 3) {
+      if (top) count_kernel<T, 3, true><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
+      else count_kernel<T, 3, false><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
+    } else {
+      if (top) count_kernel<T, 2, true><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
+      else count_kernel<T, 2, false><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
+    }
     g->launches++;
+  };
+  count(xyz, n, hook ? &hook->top : nullptr);
+  if (hook) {
+    uint64_t n_halo = 0;
+    ZB_TRY(hook->exchange(&n_halo));
+    count(xyz + n * (uint64_t)g->ndim, n_halo, nullptr);
+    n += n_halo;
   }
   {
     StageSpan span(g, ZB_STAGE_SCAN);
@@ -458,7 +481,7 @@ int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
 template <class T>
 int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* labels_any, const double* cutoff,
                  const double* inf, const double* sup, int64_t z_begin, int64_t z_end, bool sharded,
-                 const LabelSrc* label_src = nullptr) {
+                 const LabelSrc* label_src = nullptr, SlabHook<T>* hook = nullptr) {
   if (n > 2147483647ull) return fail(g, ZB_ERR_TOO_MANY, "n = %llu exceeds i32::MAX", (unsigned long long)n);
   if (n > 0 && !xyz_any) return fail(g, ZB_ERR_BAD_ARG, "xyz is NULL");
   if (cutoff) {
@@ -526,7 +549,12 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   }
   LabelSrc ls{labels, nullptr, 0u, 0xffffffffu};  // no array: label = position
   if (label_src) ls = *label_src;
-  ZB_TRY(build_sorted<T>(g, xyz, ls, n));
+  if (hook) {  // window-relative layers of the rank's own slab [z_begin, z_end - 1]
+    const int ax = g->ndim - 1;
+    hook->top.first = (int)(z_begin - g->wlo[ax]);
+    hook->top.top = (int)(z_end - 1 - g->wlo[ax]);
+  }
+  ZB_TRY(build_sorted<T>(g, xyz, ls, n, hook));  // n grows by the halo rows the hook received
 
   // home-cell range of the pair kernels
   {
@@ -1520,22 +1548,39 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
   const int64_t nz = g->shape[ax];
   const int64_t z_begin = (int64_t)N.rank * nz / N.world, z_end = (int64_t)(N.rank + 1) * nz / N.world;
 
-  // 2. halo: top layer of this slab -> rank + 1, top layer of rank - 1 -> behind the local rows
+  // 2 + 3. sharded rebuild with the imposed box.  K2 over the local rows also extracts this slab's top
+  //    layer (no extra pass over the input); the hook then trades halos -- top layer -> rank + 1, top
+  //    layer of rank - 1 -> behind the local rows -- and K2 counts the few received rows; K3, K4 run
+  //    over local + halo rows.  Labels come from (offset + i | halo labels).
   const size_t block = (halo_cap + 1) * 4 * sizeof(T);
   ZB_TRY(reserve(g, g->halo_send, block));
   ZB_TRY(reserve(g, g->halo_recv, block));
   ZB_TRY(reserve(g, g->halo_labels, std::max<uint64_t>(halo_cap, 1) * 4));
-  ZB_TRY(zb_slab_top_layer(g, xyz, n_local, inf[ax], g->cutoff, z_begin, z_end, label_offset, g->halo_send.p, halo_cap,
-                           nullptr, nullptr));
-  const bool up = N.rank + 1 < N.world, down = N.rank > 0;
+  // slab_count / slab_flag live apart from the rebuild's counters
+  ZB_CUDA(cudaMemsetAsync(&g->misc->slab_count, 0, 2 * sizeof(uint32_t), g->stream));
   uint64_t n_halo = 0;
-  if (up || down) {
-    ZB_NCCL(N.GroupStart());
-    if (up) ZB_NCCL(N.Send(g->halo_send.p, block, ncclChar, N.rank + 1, N.comm, g->stream));
-    if (down) ZB_NCCL(N.Recv(g->halo_recv.p, block, ncclChar, N.rank - 1, N.comm, g->stream));
-    ZB_NCCL(N.GroupEnd());
-  }
-  if (down) {
+  SlabHook<T> hook;
+  hook.top.out = static_cast<T*>(g->halo_send.p);
+  hook.top.cap = (uint32_t)std::min<uint64_t>(halo_cap, 0xfffffff0ull);
+  hook.top.count = &g->misc->slab_count;
+  hook.top.bad = reinterpret_cast<int*>(&g->misc->slab_flag);
+  hook.top.label_offset = label_offset;
+  hook.n_cap = std::min<uint64_t>(cap_rows, n_local + halo_cap);
+  hook.exchange = [&](uint64_t* got) -> int {
+    *got = 0;
+    // the block header (row 0) carries the row count to the receiver
+    halo_header_kernel<T><<<1, 1, 0, g->stream>>>(&g->misc->slab_count, hook.top.cap, static_cast<T*>(g->halo_send.p));
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    g->slab_check_pending = true;
+    const bool up = N.rank + 1 < N.world, down = N.rank > 0;
+    if (up || down) {
+      ZB_NCCL(N.GroupStart());
+      if (up) ZB_NCCL(N.Send(g->halo_send.p, block, ncclChar, N.rank + 1, N.comm, g->stream));
+      if (down) ZB_NCCL(N.Recv(g->halo_recv.p, block, ncclChar, N.rank - 1, N.comm, g->stream));
+      ZB_NCCL(N.GroupEnd());
+    }
+    if (!down) return ZB_OK;
     ZB_CUDA(cudaMemcpyAsync(g->h_red, g->halo_recv.p, sizeof(T), cudaMemcpyDeviceToHost, g->stream));
     ZB_CUDA(cudaStreamSynchronize(g->stream));
     n_halo = (uint64_t) * reinterpret_cast<const T*>(g->h_red);
@@ -1552,11 +1597,11 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
       g->launches++;
       ZB_CUDA(cudaGetLastError());
     }
-  }
-
-  // 3. sharded rebuild with the imposed box (K2-K4); labels come from (offset + i | halo labels)
+    *got = n_halo;
+    return ZB_OK;
+  };
   LabelSrc ls{nullptr, static_cast<const uint32_t*>(g->halo_labels.p), label_offset, (uint32_t)n_local};
-  ZB_TRY(rebuild_impl<T>(g, xyz, n_local + n_halo, nullptr, nullptr, inf, sup, z_begin, z_end, true, &ls));
+  ZB_TRY(rebuild_impl<T>(g, xyz, n_local, nullptr, nullptr, inf, sup, z_begin, z_end, true, &ls, &hook));
   g->n_local = n_local;
   g->n_halo = n_halo;
   if (out) {
