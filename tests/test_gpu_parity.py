@@ -656,3 +656,29 @@ def test_stable_cell_storage_matches_reference_order(zb):
         assert np.array_equal(cg.cell_storage()[0], labels)   # reproducible layout
         _, e64, _ = og.lj_energy(CMP_LT, cutoff)
         assert abs(e1 - e64) <= F64_RTOL * abs(e64)
+
+
+def test_stage_profile_mask_and_rebuild_mut_shrinking_box(zb):
+    """zb_grid_profile's stage mask records only the selected launches; rebuild_mut over clouds whose
+    cell count shrinks and grows again (the table is cleared speculatively for the PREVIOUS build's
+    size while the bounding box travels to the host) stays exact."""
+    pts, cutoff = _cloud("lj", 30000, np.float64)
+    cg = zb.CellGrid(pts, cutoff)
+    cg.profile(True, stages=["pair_lj"])
+    cg.rebuild_mut(pts, None)
+    cg.lj_energy(cutoff, "lt")
+    st = cg.profile_read()
+    assert st["pair_lj"][1] == 1 and st["pair_lj"][0] > 0
+    assert all(v[1] == 0 for k, v in st.items() if k != "pair_lj")
+    cg.profile(True)
+    cg.rebuild_mut(pts, None)
+    st = cg.profile_read()
+    assert st["count"][1] == 1 and st["scatter"][1] == 1 and st["bbox"][1] == 1
+    cg.profile(False)
+    for m in (30000, 2000, 50, 30000, 1, 12000):   # smaller boxes reuse the pre-cleared table, larger ones re-clear
+        sub = pts[:m]
+        cg.rebuild_mut(sub, None)
+        og = OracleCellGrid(sub, cutoff)
+        assert cg.info().n_cells == og.info()["n_cells"]
+        assert cg.pair_count(cutoff, "le") == og.pair_count(CMP_LE, cutoff)
+        assert np.array_equal(canonical_pairs(cg.particle_pairs(cutoff, "lt")), og.pairs_canonical(CMP_LT, cutoff))

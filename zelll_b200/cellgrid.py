@@ -540,8 +540,14 @@ class CellGrid:
             self._check(self._lib.zb_grid_set_stream(self._h, C.c_void_p(cuda_stream)))
             self._stream = cuda_stream
 
-    def profile(self, enable: bool = True) -> None:
-        self._check(self._lib.zb_grid_profile(self._h, int(enable)))
+    def profile(self, enable: bool = True, stages=None) -> None:
+        """Per-stage device timing on / off; `stages` (names from _ffi.STAGES) restricts the recording."""
+        code = int(bool(enable))
+        if enable and stages is not None:
+            code = 0
+            for name in stages:
+                code |= 1 << (_ffi.STAGES.index(name) + 1)
+        self._check(self._lib.zb_grid_profile(self._h, code))
 
     def profile_read(self) -> dict:
         """{stage: (summed device ms, launches)} since profile(True)."""

@@ -151,6 +151,9 @@ struct zb_grid {
   bool info_pending = false;
   struct OccEntry { const void* kern; size_t smem; int occ; };
   std::vector<OccEntry> occ_cache;  // launch_pairs: occupancy per (kernel, dynamic smem)
+  cudaEvent_t bbox_event = nullptr;  // fires when the bounding box has reached the host
+  bool built_once = false;           // the table / scan state hold a previous build (sizes in ncells)
+  uint32_t precleared = 0;           // cells whose table entries (+ scan state, counters) were cleared speculatively
   // zb_grid_pairs: per-tile counts of the last sizing pass (still in tile_counts)
   bool emit_cache_valid = false;
   uint64_t emit_cache_build = 0, emit_cache_total = 0;
@@ -159,7 +162,7 @@ struct zb_grid {
   PairPlan emit_cache_plan{};
 
   // optional per-stage device timing (zb_grid_profile): cudaEvent pairs around the hot launches
-  bool profile = false;
+  uint32_t profile = 0;  // bit s: record stage s
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> ev_free;
@@ -184,7 +187,7 @@ struct StageSpan {
   zb_grid* g;
   cudaEvent_t b = nullptr;
   StageSpan(zb_grid* g_, int stage) : g(g_) {
-    if (!g->profile) return;
+    if (!(g->profile >> stage & 1u)) return;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (auto& e : ev) {
       if (!g->ev_free.empty()) {
@@ -305,9 +308,25 @@ int launch_bbox(zb_grid* g, const T* xyz, uint64_t n) {
 }
 
 template <class T>
-int fetch_bbox(zb_grid* g, double* out6) {
+int fetch_bbox(zb_grid* g, double* out6, bool preclear) {
   ZB_CUDA(cudaMemcpyAsync(g->h_misc->out6, g->misc->out6, 6 * sizeof(T), cudaMemcpyDeviceToHost, g->stream));
-  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (!g->bbox_event) ZB_CUDA(cudaEventCreateWithFlags(&g->bbox_event, cudaEventDisableTiming));
+  ZB_CUDA(cudaEventRecord(g->bbox_event, g->stream));
+  // While the box travels to the host the GPU would idle: clear the count table, scan state and
+  // counters for the PREVIOUS build's cell count now (rebuild_mut of a similar cloud needs exactly
+  // that); build_sorted clears again only if this box turns out to need more cells.
+  g->precleared = 0;
+  if (preclear && g->built_once && g->table.p && g->scan_state.p && g->ncells > 0) {
+    const size_t nc = g->ncells;
+    const size_t ntile = (nc + kScanTile - 1) / kScanTile;
+    if ((4 + nc) * 4 <= g->table.cap && ntile * sizeof(unsigned long long) <= g->scan_state.cap) {
+      ZB_CUDA(cudaMemsetAsync(g->table.p, 0, (4 + nc) * 4, g->stream));
+      ZB_CUDA(cudaMemsetAsync(g->scan_state.p, 0, ntile * sizeof(unsigned long long), g->stream));
+      ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 3 * sizeof(uint32_t), g->stream));
+      g->precleared = (uint32_t)nc;
+    }
+  }
+  ZB_CUDA(cudaEventSynchronize(g->bbox_event));
   const T* t = reinterpret_cast<const T*>(g->h_misc->out6);
   for (int d = 0; d < 6; ++d) out6[d] = (double)t[d];
   return ZB_OK;
@@ -374,10 +393,14 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t& n, 
   const uint32_t ntile = (uint32_t)((nc + kScanTile - 1) / kScanTile);
   ZB_TRY(reserve(g, g->scan_state, (size_t)ntile * sizeof(unsigned long long)));
 
-  // one memset clears the 4 leading entries (csr[0] = 0) and all counts
-  ZB_CUDA(cudaMemsetAsync(g->table.p, 0, (4 + (size_t)nc) * 4, g->stream));
-  ZB_CUDA(cudaMemsetAsync(g->scan_state.p, 0, (size_t)ntile * sizeof(unsigned long long), g->stream));
-  ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 3 * sizeof(uint32_t), g->stream));  // tile_counter, nonempty, flags
+  if (g->precleared == 0 || g->precleared < nc) {  // not already cleared while the box was fetched
+    // one memset clears the 4 leading entries (csr[0] = 0) and all counts
+    ZB_CUDA(cudaMemsetAsync(g->table.p, 0, (4 + (size_t)nc) * 4, g->stream));
+    ZB_CUDA(cudaMemsetAsync(g->scan_state.p, 0, (size_t)ntile * sizeof(unsigned long long), g->stream));
+    ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 3 * sizeof(uint32_t), g->stream));  // tile_counter, nonempty, flags
+  }
+  g->precleared = 0;
+  g->built_once = true;
 
   const GridParams<T> p = make_params<T>(g);
   uint32_t* cursor = cursor_ptr(g);
@@ -492,6 +515,7 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   g->built = false;
   g->build_id++;
   g->emit_cache_valid = false;
+  g->precleared = 0;
   if (g->info_pending) {  // the previous build's counters are about to be overwritten
     ZB_CUDA(cudaEventSynchronize(g->info_event));
     g->info_pending = false;
@@ -517,7 +541,7 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
     } else {
       ZB_TRY(launch_bbox<T>(g, xyz, n));
       double o[6];
-      ZB_TRY(fetch_bbox<T>(g, o));
+      ZB_TRY(fetch_bbox<T>(g, o, true));
       for (int d = 0; d < 3; ++d) {
         g->inf[d] = d < g->ndim ? o[d] : 0.0;
         g->sup[d] = d < g->ndim ? o[3 + d] : 0.0;
@@ -902,6 +926,7 @@ void zb_grid_destroy(zb_grid* g) {
     free_buf(sl.buf);
   }
   if (g->info_event) cudaEventDestroy(g->info_event);
+  if (g->bbox_event) cudaEventDestroy(g->bbox_event);
   if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
   if (g->nccl.dl) dlclose(g->nccl.dl);
   if (g->h_red) cudaFreeHost(g->h_red);
@@ -1025,8 +1050,8 @@ int zb_aabb(zb_grid* g, const void* xyz, uint64_t n, double* out6) {
     return ZB_OK;
   }
   double o[6];
-  if (g->dtype == ZB_F32) ZB_TRY(fetch_bbox<float>(g, o));
-  else ZB_TRY(fetch_bbox<double>(g, o));
+  if (g->dtype == ZB_F32) ZB_TRY(fetch_bbox<float>(g, o, false));
+  else ZB_TRY(fetch_bbox<double>(g, o, false));
   for (int d = 0; d < 6; ++d) out6[d] = 0.0;
   for (int d = 0; d < g->ndim; ++d) {
     out6[d] = o[d];
@@ -1661,7 +1686,8 @@ int zb_grid_profile(zb_grid* g, int enable) {
     g->stage_ms[i] = 0.0;
     g->stage_launches[i] = 0;
   }
-  g->profile = enable != 0;
+  // 0 = off, 1 = every stage, otherwise bit (s + 1) selects stage s
+  g->profile = enable == 0 ? 0u : (enable == 1 ? 0xffffffffu : ((uint32_t)enable >> 1));
   return ZB_OK;
 }
 
