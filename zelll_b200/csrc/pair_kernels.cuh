@@ -20,21 +20,25 @@
 // and its lower halo (all cells back to cell - (w0*w1 + w0 + 1)) fit the stage buffer -- always
 // the case for the slab-shaped benchmark box -- they form ONE contiguous range of records,
 // brought into shared memory by a single TMA bulk copy (cp.async.bulk, mbarrier completion).
-// Otherwise (wide grids) the tile reads records through L1/L2 directly.  Inside a tile each warp
-// takes home cells round-robin; its 32 lanes hold 32 candidate particles j of the 5 runs in
-// registers while the home particles i are broadcast from shared memory, so every shared-memory
-// read in the inner loop is a conflict-free broadcast.
+// Otherwise (wide grids) the tile reads records through L1/L2 directly.  The grid is persistent
+// (SMs x occupancy CTAs): a CTA's first tile is blockIdx.x, every further one is claimed from a
+// global counter one tile ahead.  Inside a tile one thread per home cell first computes the cell's
+// run descriptor (CellRuns); warps then claim home cells dynamically.  A warp's 32 lanes hold up
+// to 2 x 32 candidate particles j of the 5 runs in registers while the home particles i are
+// broadcast from shared memory (explicit ld.shared through one 32-bit address register), two home
+// particles per step; the last, partial chunk of a cell is packed (2 or 4 home particles tested
+// against the same <= 16 / <= 8 candidates by different lane groups).
 //
 // Arithmetic.  dsq = (dx*dx + dy*dy) + dz*dz with separately rounded operations, exactly what
 // nalgebra::distance_squared does (benches/lj.rs:84); the TU is compiled with -fmad=false.
 //
-// f32 prefilter for f64 grids.  FP64 issue, not HBM, bounds the f64 distance test on B200 (9 DP
-// instructions per test at 4 cycles per warp instruction and SM sub-partition).  Staged tiles
-// therefore also keep every record as float4 coordinates RELATIVE to the tile's first record;
-// the test loop runs in f32 (FFMA allowed) and classifies each pair against a guard band around
-// the threshold that is wider than the worst-case f32 error (derivation at prefilter_band()).
-// Sure misses -- 80 % of the tests -- never touch the FP64 pipe; everything else is re-evaluated
-// from the f64 records with the reference's exact arithmetic, so the pair set stays bit-exact.
+// f32 prefilter for f64 grids (OPT-IN, ZB_PREFILTER=1; measured at parity with the exact loop, which
+// is bound by instruction issue and the FP64 pipe together -- DESIGN.md section 6).  Staged tiles
+// also keep every record as float4 coordinates RELATIVE to the tile's first record; the test loop
+// runs in f32 (FFMA allowed) and classifies each pair against a guard band around the threshold
+// that is wider than the worst-case f32 error (derivation at prefilter_delta()).  Sure misses --
+// 80 % of the tests -- never touch the FP64 pipe; everything else is re-evaluated from the f64
+// records with the reference's exact arithmetic, so the pair set stays bit-exact.
 #pragma once
 
 #include "common.cuh"
