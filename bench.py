@@ -106,10 +106,20 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm on the host cores (oracle = C++ restatement)
-def cpu_rebuild_lj(n: int, reps: int, warmup: int = 1):
+def host_threads() -> int:
+    """Host threads the CPU arm may use: the cores this process is allowed on, NOT OMP_NUM_THREADS
+    (torch.distributed.run exports OMP_NUM_THREADS=1 to every rank)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_rebuild_lj(n: int, reps: int, warmup: int, threads: int, layout: str = "uniform"):
     """Sequential CellGrid::new (the reference's construction is single-threaded, cellgrid.rs:187-238)
-    + par_particle_pairs-shaped LJ over all host threads (cellgrid.rs:447-451).  Returns
-    (seconds per step, in-cutoff pairs per step, threads)."""
+    + the LJ pass: threads == 1 is `particle_pairs` (benches/lj.rs:100-123), threads > 1 is
+    `par_particle_pairs` over that many rayon-style workers (cellgrid.rs:447-451, benches/iters.rs:81-85).
+    Returns (seconds per step, seconds of the rebuild alone, in-cutoff pairs per step)."""
     import oracle
 
     try:
@@ -117,34 +127,44 @@ def cpu_rebuild_lj(n: int, reps: int, warmup: int = 1):
         native = True
     except Exception:
         native = False
-    threads = max(1, min(os.cpu_count() or 1, oracle.max_threads()))
     pts = workload.generate_points_random(n)
+    if layout == "presorted":
+        pts = workload.presort_by_z(pts)
     og = oracle.OracleCellGrid(pts, CUTOFF, native=native)
-    times, pairs = [], 0
+    times, builds, pairs = [], [], 0
     for k in range(warmup + reps):
         t0 = time.perf_counter()
         og.rebuild(pts, CUTOFF)
+        t1 = time.perf_counter()
         _, _, pairs = og.lj_energy(oracle.CMP_LT, CUTOFF, nthreads=threads)
         dt = time.perf_counter() - t0
         if k >= warmup:
             times.append(dt)
-    return sum(times) / len(times), pairs, threads
+            builds.append(t1 - t0)
+    return sum(times) / len(times), sum(builds) / len(builds), pairs
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU arm runs on rank 0 alone
-    sec, pairs, threads = cpu_rebuild_lj(CPU_SAMPLE_N, max(1, args.steps), max(1, args.warmup))
+    threads = host_threads()
+    n = N_PER_GPU if args.n_per_gpu is None else args.n_per_gpu
+    # one step = the stated per-GPU batch (n = 10^7: the whole workload at N = 1); at N > 1 the job is
+    # N such batches, the CPU rate is measured on one of them
+    n_cpu = min(n, 10_000_000)
+    sec, sec_build, pairs = cpu_rebuild_lj(n_cpu, max(1, args.steps), max(1, args.warmup), threads, args.layout)
     value = pairs / sec
-    sample = (f"n={CPU_SAMPLE_N} slice of the n={N_PER_GPU} box (same density and cutoff); sequential rebuild + "
-              f"{threads}-thread LJ pass per step")
+    sample = (f"n={n_cpu} particles per step ({'the full single-GPU batch' if n_cpu == n else 'slice of the per-GPU batch'}"
+              f"{'' if args.gpus == 1 else f', 1 of the {args.gpus} slabs of the job'}), same density, cutoff and layout; "
+              f"sequential rebuild ({sec_build * 1e3:.0f} ms) + {threads}-thread par_particle_pairs LJ pass per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(args.gpus, N_PER_GPU),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": _config(args.gpus, n, args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "Rust reference not buildable here (no cargo/rustc): C++ restatement of its algorithm (oracle/)",
@@ -152,24 +172,34 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def _config(n_gpus: int, n_per_gpu: int):
+def _config(n_gpus: int, n_per_gpu: int, args=None):
+    layout = getattr(args, "layout", "uniform")
+    scaling = getattr(args, "scaling", "weak")
+    box_xy = getattr(args, "box_xy", 3)
     return {
-        "workload": f"rebuild+lj: CellGrid rebuild_mut + LJ energy (dsq < c^2), n={n_per_gpu:.0e} f64 particles per GPU, "
-                    f"uniform random box 30x30x(n/9), cutoff 10 (benches/lj.rs; BASELINE.json configs[2]/north_star 10^7)",
-        "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * n_gpus, "cutoff": CUTOFF,
-        "l2": "inputs (240 MB points + 320 MB cell-sorted records per GPU) exceed the 126 MB L2; no explicit flush",
+        "workload": f"rebuild+lj: CellGrid rebuild_mut + LJ energy (dsq < c^2), n={n_per_gpu:.3g} f64 particles per GPU, "
+                    f"{layout} box {10 * box_xy}x{10 * box_xy}xL at 10 particles per cutoff^3, cutoff 10 (benches/lj.rs; "
+                    f"BASELINE.json configs[2]/north_star 10^7" + ("; configs[3] presorted" if layout == "presorted" else "")
+                    + ("; configs[4] scaling" if n_gpus > 1 or n_per_gpu != N_PER_GPU else "") + ")",
+        "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * n_gpus, "cutoff": CUTOFF, "layout": layout, "scaling": scaling,
+        "box_cells_xy": box_xy,
+        "l2": f"inputs ({24 * n_per_gpu / 1e6:.0f} MB points + {32 * n_per_gpu / 1e6:.0f} MB cell-sorted records per GPU) "
+              f"exceed the 126 MB L2; no explicit flush" if n_per_gpu >= 4_000_000 else
+              "inputs smaller than L2: every step rewrites the cell-sorted records, no explicit flush",
         "parallelism": "single GPU" if n_gpus == 1 else f"z-slab decomposition over {n_gpus} GPUs, halo send/recv + all-reduce (NCCL)",
     }
 
 
 # ---------------------------------------------------------------------------------------------
-def slab_points(torch, rank: int, world: int, n_per: int, device, spare: int):
+def slab_points(torch, rank: int, world: int, n_per: int, device, spare: int, box_xy: int = 3, presorted: bool = False):
     """This rank's slab of the global benchmark box, generated on the device (10^9 x 24 B does not
-    fit host RAM).  Global box: 30 x 30 x L, L = world * n_per / 9, centred; layers of height
-    `cutoff` are split evenly, and every rank draws uniformly inside its own layers.  Two pinned
-    corner particles make the global bounding box (hence the layer count) deterministic."""
+    fit host RAM).  Global box: a x a x L with a = 10 * box_xy and L = world * n_per / (density * a^2),
+    centred; layers of height `cutoff` are split evenly, and every rank draws uniformly inside its own
+    layers.  Two pinned corner particles make the global bounding box (hence the layer count)
+    deterministic.  presorted: the slab's rows are sorted by z (examples/cachemisses.rs:57-59)."""
     total = world * n_per
-    L = total / 9.0
+    a = CUTOFF * box_xy
+    L = total * CUTOFF**3 / 10.0 / (a * a)
     nz = int(np.floor(L / CUTOFF)) + 1
     from zelll_b200.sharded import slab_bounds
 
@@ -178,20 +208,70 @@ def slab_points(torch, rank: int, world: int, n_per: int, device, spare: int):
     g.manual_seed(workload.REFERENCE_SEED % (2**63) + rank)
     buf = torch.empty((n_per + spare, 3), dtype=torch.float64, device=device)
     u = torch.rand((n_per, 3), dtype=torch.float64, device=device, generator=g)
-    buf[:n_per, 0] = (u[:, 0] - 0.5) * 30.0
-    buf[:n_per, 1] = (u[:, 1] - 0.5) * 30.0
+    if presorted:
+        u[:, 2] = torch.sort(u[:, 2]).values
+    buf[:n_per, 0] = (u[:, 0] - 0.5) * a
+    buf[:n_per, 1] = (u[:, 1] - 0.5) * a
     zmax_layers = min(ze, L / CUTOFF)  # the last slab ends where the box ends
     lo, hi = zb + 1e-7, zmax_layers - 1e-7
     buf[:n_per, 2] = -L / 2.0 + CUTOFF * (lo + u[:, 2] * (hi - lo))
     if rank == 0:
-        buf[0] = torch.tensor([-15.0, -15.0, -L / 2.0], dtype=torch.float64)
+        buf[0] = torch.tensor([-a / 2.0, -a / 2.0, -L / 2.0], dtype=torch.float64)
     if rank == world - 1:
-        # just inside the open upper faces: uniform draws never reach +15, the grid stays 3 x 3 x nz cells
-        # like the single-GPU box (a corner AT +15 would open a fourth, empty cell column in x and y)
-        buf[n_per - 1] = torch.tensor([15.0 - 1e-9, 15.0 - 1e-9, -L / 2.0 + CUTOFF * (nz - 1) + 0.5 * (L - CUTOFF * (nz - 1))],
+        # just inside the open upper faces: uniform draws never reach +a/2, the grid stays box_xy^2 x nz cells
+        # like the single-GPU box (a corner AT +a/2 would open one more, empty cell column in x and y)
+        buf[n_per - 1] = torch.tensor([a / 2.0 - 1e-9, a / 2.0 - 1e-9, -L / 2.0 + CUTOFF * (nz - 1) + 0.5 * (L - CUTOFF * (nz - 1))],
                                       dtype=torch.float64)
     del u
     return buf
+
+
+def parity_check(torch, dist, rank: int, world: int, local_rank: int, device, n: int = 200_000):
+    """configs[4] parity under the driver: the native NCCL slab path (the one the timed region runs)
+    against the single-GPU grid of the same cloud -- all-reduced pair counts (`<` and `<=`), LJ energy
+    to 1e-10, and the union of the sharded pair lists bit-exact in canonical form."""
+    import zelll_b200
+    from zelll_b200.sharded import NativeSlabGrid, slab_bounds
+
+    def canonical(p):
+        p = np.asarray(p).reshape(-1, 2).astype(np.uint64)
+        key = (np.minimum(p[:, 0], p[:, 1]) << np.uint64(32)) | np.maximum(p[:, 0], p[:, 1])
+        key.sort()
+        return key
+
+    pts = workload.generate_points_random(n)
+    single = zelll_b200.CellGrid(pts, CUTOFF, device=local_rank)
+    e_ref, m_ref = single.lj_energy(CUTOFF, "lt", return_pairs=True)
+    c_ref = single.pair_count(CUTOFF, "le")
+    want = canonical(single.particle_pairs(CUTOFF, "lt"))
+    order = np.argsort(pts[:, 2], kind="stable")
+    spts = pts[order]
+    inf_z = spts[0, 2]
+    nz = int(np.floor((spts[-1, 2] - inf_z) / CUTOFF)) + 1
+    layer = np.floor((spts[:, 2] - inf_z) / CUTOFF).astype(np.int64)
+    zb, ze = slab_bounds(nz, world, rank)
+    sel = np.nonzero((layer >= zb) & (layer < ze))[0]
+    buf = torch.zeros((len(sel) + 4096, 3), dtype=torch.float64, device=device)
+    buf[: len(sel)] = torch.from_numpy(spts[sel]).to(device)
+    ng = NativeSlabGrid(dtype=np.float64, device=local_rank)
+    ng.rebuild_slab_local(buf, len(sel), CUTOFF, label_offset=int(sel[0]) if len(sel) else 0)
+    e, m = ng.lj_energy_allreduce(CUTOFF, "lt", return_pairs=True)
+    ct = torch.tensor([ng.pair_count(CUTOFF, "le")], dtype=torch.int64, device=device)
+    dist.all_reduce(ct)
+    local_pairs = order.astype(np.uint64)[ng.particle_pairs(CUTOFF, "lt").astype(np.int64)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.asarray(local_pairs, dtype=np.uint64))
+    got = canonical(np.concatenate(gathered))
+    rel = abs(e - e_ref) / abs(e_ref)
+    res = {"world": world, "n": n, "path": "native NCCL slab step vs single-GPU grid",
+           "pairs": bool(m == m_ref), "pairs_le": bool(int(ct.item()) == c_ref),
+           "pair_set": bool(np.array_equal(got, want)), "energy_rel": rel}
+    res["ok"] = bool(res["pairs"] and res["pairs_le"] and res["pair_set"] and rel <= 1e-10)
+    flag = torch.tensor([0 if res["ok"] else 1], dtype=torch.int64, device=device)
+    dist.all_reduce(flag)
+    res["ok"] = bool(flag.item() == 0)
+    del ng, single
+    return res
 
 
 def _bind_to_gpu_numa_node(index: int) -> None:
@@ -234,8 +314,22 @@ def run_ours(args):
     if distributed:
         dist.init_process_group("nccl", device_id=device)
 
-    n_per = args.n_per_gpu
+    if args.scaling == "strong":
+        n_total = args.n_total if args.n_total else N_PER_GPU
+        n_per = n_total // world
+    else:
+        n_per = N_PER_GPU if args.n_per_gpu is None else args.n_per_gpu
     steps, warmup = args.steps, max(args.warmup, 3)
+    box_xy = args.box_xy
+    # N > 1: the native NCCL path is checked against the single-GPU grid BEFORE anything is timed
+    parity = None
+    if distributed and not args.no_parity:
+        parity = parity_check(torch, dist, rank, world, local_rank, device)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-GPU parity check failed", "parity_check": parity}))
+            dist.destroy_process_group()
+            raise SystemExit(3)
     hbm_peak, peak_src = _peaks()
     stream = torch.cuda.current_stream(device)
 
@@ -246,7 +340,10 @@ def run_ours(args):
 
     # ---- set-up: points resident in HBM, pinned host copy for the e2e leg ------------------
     if not distributed:
-        host_pts = workload.generate_points_random(n_per)
+        a = CUTOFF * box_xy
+        host_pts = workload.generate_points_random(n_per, vol=(a, a, n_per * CUTOFF**3 / 10.0 / (a * a)))
+        if args.layout == "presorted":
+            host_pts = workload.presort_by_z(host_pts)
         pinned = torch.from_numpy(host_pts).pin_memory()
         dev_pts = pinned.to(device, non_blocking=True)
         grid = zelll_b200.CellGrid(dev_pts, CUTOFF, device=local_rank)
@@ -272,8 +369,10 @@ def run_ours(args):
 
         engine = grid
     else:
-        spare = 8192  # the halo is one 3x3-cell layer (~90 particles)
-        buf = slab_points(torch, rank, world, n_per, device, spare)
+        # the halo is one layer of box_xy^2 cells, ~10 particles each (3x3: ~90 rows)
+        halo_cap = max(8192, int(box_xy * box_xy * 10 * 1.5) + 4096)
+        spare = halo_cap
+        buf = slab_points(torch, rank, world, n_per, device, spare, box_xy, args.layout == "presorted")
         dg = NativeSlabGrid(dtype=np.float64, device=local_rank)   # NCCL driven from the C ABI
         pinned = None
         if not args.no_e2e:
@@ -282,7 +381,7 @@ def run_ours(args):
         engine = dg
 
         def step_resident():
-            dg.rebuild_slab_local(buf, n_per, CUTOFF, label_offset=rank * n_per)
+            dg.rebuild_slab_local(buf, n_per, CUTOFF, label_offset=rank * n_per, halo_cap=halo_cap)
             return dg.lj_energy_allreduce(CUTOFF, "lt", return_pairs=True)
 
         # e2e: this rank's slab streams from pinned host memory, double-buffered on a side stream
@@ -301,7 +400,7 @@ def run_ours(args):
             stream.wait_stream(copy_stream)                  # this step's H2D has landed
             with torch.cuda.stream(copy_stream):             # next frame's H2D overlaps this step's kernels
                 nxt[:n_per].copy_(pinned, non_blocking=True) # (nxt was read by the build before last: done)
-            dg.rebuild_slab_local(cur, n_per, CUTOFF, label_offset=rank * n_per)
+            dg.rebuild_slab_local(cur, n_per, CUTOFF, label_offset=rank * n_per, halo_cap=halo_cap)
             return dg.lj_energy_allreduce(CUTOFF, "lt", return_pairs=True)
 
     engine.use_stream(stream.cuda_stream)
@@ -384,25 +483,48 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": kernels[dom]["ms_per_launch"],
-                "candidate_tests_per_s": 81.6 * n_local / (kernels[dom]["ms_per_launch"] * 1e-3) if dom == "pair_lj" else None,
+                "candidate_tests_per_s": 81.6 * n_local / (kernels[dom]["ms_per_launch"] * 1e-3) if dom == "pair_lj" and box_xy == 3 else None,
                 "ncu": ncu_note,
                 "step_algorithmic_GB": 101.6 * n_local / 1e9,
                 "step_frac_of_hbm_peak": 101.6 * n_local / 1e9 / (ms_step * 1e-3) / hbm_peak}
 
+    # FP64 issue ceiling of the exact-arithmetic part (profiles/fp64_peak.json: DADD/DMUL microbenchmark on
+    # this GPU model): the reference's test is 9 separately rounded f64 operations per candidate pair
+    fpath = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if dom.startswith("pair") and os.path.exists(fpath):
+        with open(fpath) as f:
+            fj = json.load(f)
+        peak_ops = float(fj["dadd"]["lane_ops_per_s"])
+        tests_s = roofline["candidate_tests_per_s"] or 0.0
+        roofline["fp64"] = {"ops_per_test": 9, "achieved_ops_s": 9 * tests_s, "peak_ops_s": peak_ops,
+                            "frac": 9 * tests_s / peak_ops, "peak_source": "profiles/fp64_peak.json (scripts/issue_peaks.cu, DADD)",
+                            "note": "equivalent f64 operations of the reference's exact test per second; above 1.0 means the "
+                                    "f32 prefilter keeps most tests off the FP64 pipe"}
+
     # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------------
     cpu = None
     if not distributed and not args.no_cpu:
-        sec, cpairs, threads = cpu_rebuild_lj(CPU_SAMPLE_N, reps=5, warmup=1)
-        cpu = {"value": cpairs / sec, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"n={CPU_SAMPLE_N} slice of the same box, 5 steps of sequential rebuild + {threads}-thread LJ "
-                         f"pass (C++ restatement of the reference; the Rust crate cannot be built here)",
-               "ms_per_step_sample": sec * 1e3}
+        nthr = host_threads()
+        par = min(nthr, 16)  # benches/iters.rs:81-85 sweeps rayon pools up to 16 threads
+        sec_p, build_p, cpairs = cpu_rebuild_lj(CPU_SAMPLE_N, reps=5, warmup=1, threads=par, layout=args.layout)
+        sec_s, build_s, _ = cpu_rebuild_lj(CPU_SAMPLE_N, reps=2, warmup=1, threads=1, layout=args.layout)
+        sec_a = sec_p
+        if nthr != par:
+            sec_a, _, _ = cpu_rebuild_lj(CPU_SAMPLE_N, reps=5, warmup=1, threads=nthr, layout=args.layout)
+        cpu = {"value": cpairs / sec_a, "unit": UNIT, "cores": nthr, "kind": "port",
+               "sample": f"n={CPU_SAMPLE_N} slice of the same box, sequential rebuild + {nthr}-thread LJ pass per step "
+                         f"(C++ restatement of the reference; the Rust crate cannot be built here)",
+               "ms_per_step_sample": sec_a * 1e3, "host_cpus": os.cpu_count(),
+               "sequential": {"value": cpairs / sec_s, "cores": 1, "ms_per_step_sample": sec_s * 1e3,
+                              "ms_rebuild_sample": build_s * 1e3, "shape": "benches/lj.rs:100-123 (CellGrid::new + particle_pairs)"},
+               "parallel": {"value": cpairs / sec_p, "cores": par, "ms_per_step_sample": sec_p * 1e3,
+                            "ms_rebuild_sample": build_p * 1e3, "shape": "benches/iters.rs:81-85 (par_particle_pairs, min(nproc,16) threads)"}}
 
     total_pairs = int(pairs)
     line = {
         "metric": METRIC, "value": total_pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": _config(world, n_per),
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": _config(world, n_per, args),
         "e2e": None if args.no_e2e else {"value": int(pairs_e) / (ms_step_e2e * 1e-3), "unit": UNIT,
                                          "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": n_per * 24 * world,
                                          "d2h_bytes_per_step": 16 * world},
@@ -410,6 +532,8 @@ def run_ours(args):
         "clocks": clocks, "pairs_per_step": total_pairs, "energy": energy,
         "particles_per_s": n_per * world / (ms_step * 1e-3),
     }
+    if parity is not None:
+        line["parity_check"] = parity
     print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
@@ -421,7 +545,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--n-per-gpu", type=lambda v: int(float(v)), default=None, help="weak scaling: particles per GPU (default 10^7)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--n-total", type=lambda v: int(float(v)), default=None, help="strong scaling: total particles (default 10^7)")
+    ap.add_argument("--layout", default="uniform", choices=["uniform", "presorted"],
+                    help="presorted = rows sorted by z (examples/cachemisses.rs:57-59, BASELINE.json configs[3])")
+    ap.add_argument("--box-xy", type=int, default=3, help="box width in cells along x and y (3 = benches/lj.rs; e.g. 300 for a wide halo)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the pre-timing parity check")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (very large --n-per-gpu runs)")
     args = ap.parse_args()

@@ -98,6 +98,24 @@ G["doctest_three_points"] = {
     "points_2d": [[0.0, 0.0], [1.0, 2.0], [0.0, 0.1]],
 }
 
+# surface-sampling/src/sdf/numdual.rs:107-192  test_sdf_autodiff: the one reference-held FLOATING-POINT
+# known answer on this path.  sdf(x) = -sigma * ln(sum exp(-d/r)) over query_neighbors(x) filtered by
+# d <= cutoff (numdual.rs:17-58), sigma = sum(r exp(-d)) / sum(exp(-d)); every atom is
+# Element::default() = Carbon, radius 1.70 (atom.rs:3-6, 17-21); CellGrid cutoff 1.0 (numdual.rs:176).
+G["test_sdf_autodiff"] = {
+    "cite": "surface-sampling/src/sdf/numdual.rs:107-192; surface-sampling/src/atom.rs:3-28",
+    "cutoff": 1.0, "radius": 1.70,
+    "points": [
+        [0.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [1.0, 1.0, 0.0],
+        [0.0, 1.0, 1.0], [1.0, 0.0, 1.0], [1.0, 1.0, 1.0], [0.5, 0.5, 0.5], [1.5, 1.5, 1.5],
+    ],
+    "reference_values": [
+        -2.012457244274712, -2.012457244274712, -2.012457244274712, -2.012457244274712,
+        -2.012457244274712, -2.012457244274712, -2.012457244274712, -2.2994776285300675,
+        -2.990326826730122, -0.7998983683589523,
+    ],
+}
+
 here = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(here, "reference_known_answers.json"), "w") as f:
     json.dump(G, f, indent=1, sort_keys=True)

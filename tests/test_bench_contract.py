@@ -9,8 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_contract_line():
-    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: the arm must not inherit it
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--n-per-gpu", "300000"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -20,7 +22,9 @@ def test_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["unit"] == "pairs/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))  # all host threads, whatever OMP_NUM_THREADS says
+    assert d["config"]["n_per_gpu"] == 300000 and "n=300000" in d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
 

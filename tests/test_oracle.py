@@ -232,3 +232,29 @@ def test_query_neighbors_full_shell():
         dsq = (d[:, 0] ** 2 + d[:, 1] ** 2) + d[:, 2] ** 2
         assert sorted(near.tolist()) == sorted(want[dsq <= 100.0].tolist())
     assert cg.query_neighbors(inf - 25.0) is None
+
+
+def sdf_from_neighbors(x, nbr_xyz, radius, cutoff):
+    """SmoothDistanceField::sdf (surface-sampling/src/sdf/numdual.rs:11-58) over the points that
+    query_neighbors(x) yielded: filter dist <= cutoff, dist == 0 handled as (1, r, 1)."""
+    d = np.sqrt(((nbr_xyz - np.asarray(x)) ** 2).sum(axis=1))
+    d = d[d <= cutoff]
+    scaled = np.where(d != 0.0, np.exp(-d / radius), 1.0).sum()
+    radii = np.where(d != 0.0, np.exp(-d) * radius, radius).sum()
+    total = np.where(d != 0.0, np.exp(-d), 1.0).sum()
+    return -(radii / total) * np.log(scaled)
+
+
+def test_reference_sdf_golden(golden):
+    """The reference's only floating-point known answer behind query_neighbors (numdual.rs:107-192)."""
+    g = golden["test_sdf_autodiff"]
+    pts = np.array(g["points"])
+    cg = OracleCellGrid(pts, g["cutoff"])
+    for x, want in zip(pts, g["reference_values"]):
+        lab = cg.query_neighbors(x)
+        assert lab is not None
+        got = sdf_from_neighbors(x, pts[lab.astype(np.int64)], g["radius"], g["cutoff"])
+        assert abs(got - want) <= 4e-16 * abs(want) * len(lab)  # summation order of the fold only
+        near = cg.query_neighbors(x, CMP_LE, g["cutoff"])
+        d = np.sqrt(((pts - x) ** 2).sum(axis=1))
+        assert sorted(near.tolist()) == np.nonzero(d <= g["cutoff"])[0].tolist()

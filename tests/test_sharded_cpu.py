@@ -92,7 +92,19 @@ def _worker(rank, world, port, mode, n, outdir):
 
         pts = workload.generate_points_random(n)
         dg = DistributedCellGrid(engine=BruteEngine(), dtype=np.float64)
-        if mode == "general":
+        if mode == "few_layers":
+            # fewer z layers than ranks: the slab-local fast path must refuse on EVERY rank (its halo
+            # chain would skip the empty slabs); the general path below handles empty slabs
+            order = np.argsort(pts[:, 2], kind="stable")
+            mine = np.array_split(np.arange(n), world)[rank]
+            buf = torch.zeros((len(mine) + 64, 3), dtype=torch.float64)
+            buf[: len(mine)] = torch.from_numpy(pts[order][mine])
+            try:
+                dg.rebuild_slab_local(buf, len(mine), CUTOFF, label_offset=int(mine[0]))
+                raise AssertionError("slab-local path accepted fewer layers than ranks")
+            except ValueError as e:
+                assert "at least one layer per rank" in str(e)
+        if mode in ("general", "few_layers"):
             # every rank holds an arbitrary (interleaved) subset with its global labels
             mine = np.arange(rank, n, world)
             dg.rebuild(torch.from_numpy(pts[mine]), CUTOFF, labels=torch.from_numpy(mine.astype(np.int64)))
@@ -150,3 +162,23 @@ def test_distributed_host_logic_gloo(mode, world):
         assert int(r["m"]) == m
         assert abs(float(r["e"]) - e64) <= 1e-10 * abs(e64)
         assert int(r["cnt"]) == og.pair_count(oracle.CMP_LE, CUTOFF)
+
+
+def test_fewer_layers_than_ranks_gloo():
+    """shape[z] < world.  slab-local refuses everywhere; the general path stays exact."""
+    import torch.multiprocessing as mp
+
+    import oracle
+
+    n, world = 150, 3  # box 30 x 30 x 16.7: two layers, three ranks
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), "few_layers", n, d), nprocs=world, join=True)
+        res = [np.load(os.path.join(d, f"r{r}.npz")) for r in range(world)]
+    pts = workload.generate_points_random(n)
+    og = oracle.OracleCellGrid(pts, CUTOFF)
+    assert og.info()["shape"][2] < world
+    got = oracle.canonical_pairs(np.concatenate([r["pairs"] for r in res]))
+    assert np.array_equal(got, og.pairs_canonical(oracle.CMP_LT, CUTOFF))
+    _, e64, m = og.lj_energy(oracle.CMP_LT, CUTOFF)
+    for r in res:
+        assert int(r["m"]) == m and abs(float(r["e"]) - e64) <= 1e-10 * abs(e64)

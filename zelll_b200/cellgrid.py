@@ -317,6 +317,10 @@ class CellGrid:
                 return  # a converted copy would not be the array rebuild() sees
             if a.shape[0]:
                 self._check(self._lib.zb_grid_prefetch(self._h, a.ctypes.data, a.shape[0]))
+                # the copy is asynchronous and the slot is matched by address: keep the arrays of the two
+                # staging slots alive so neither the DMA nor a later match can see reused memory.  The
+                # caller must not modify `particles` until the rebuild that consumes it.
+                self._prefetched = (getattr(self, "_prefetched", ()) + (particles,))[-2:]
 
     def prefetch_wait(self) -> None:
         """Order this grid's stream behind the copies `prefetch` has started (zb_grid_prefetch_wait)."""

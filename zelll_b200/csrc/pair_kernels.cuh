@@ -1048,11 +1048,13 @@ __global__ void tile_list_kernel(const uint32_t* __restrict__ csr, uint32_t home
   if (live) list[base + __popc(b & lanemask_lt())] = t;
 }
 
-// (energy, pair count) -> two doubles for one all-reduce (the count is exact in f64 below 2^53)
+// (energy, pair count, error flag = 0) -> three doubles for one all-reduce (the count is exact in f64
+// below 2^53; a rank whose step failed contributes (0, 0, 1) from the host instead)
 __global__ void pack_energy_count_kernel(const double* __restrict__ e, const unsigned long long* __restrict__ c,
-                                         double* __restrict__ out2) {
-  out2[0] = *e;
-  out2[1] = (double)*c;
+                                         double* __restrict__ out3) {
+  out3[0] = *e;
+  out3[1] = (double)*c;
+  out3[2] = 0.0;
 }
 
 // exclusive scan of the per-tile pair counts (a few 10^4 entries): one block, serial over chunks

@@ -108,6 +108,7 @@ struct zb_grid {
     uint64_t n = 0;
     cudaEvent_t copied = nullptr; // recorded on the copy stream after the H2D
     cudaEvent_t released = nullptr; // recorded on the main stream after the build that read the slot
+    int age = 0;                  // rebuilds that passed this armed slot by (dropped at 2: it was never meant for them)
   } pre[2];
   cudaStream_t copy_stream = nullptr;
   int pre_in_use = -1;            // slot the current / last build read from
@@ -125,6 +126,12 @@ struct zb_grid {
   Misc* misc = nullptr;       // device
   Misc* h_misc = nullptr;     // pinned host mirror for small read-backs
   uint32_t pair_ntiles_cap = 0;
+  // experiment knobs, read from the environment ONCE at zb_grid_create (never on the launch path)
+  struct Tune {
+    bool prefilter = false;    // ZB_PREFILTER=1: f64 grids run staged tiles through the f32 prefilter
+    uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
+    uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
+  } tune;
 
   // native multi-GPU step (zb_comm_*): NCCL entry points resolved at run time from the NCCL the
   // process already uses (torch's), so the library has no link-time NCCL dependency
@@ -473,8 +480,13 @@ int track_keys(zb_grid* g) {
   return ZB_OK;
 }
 
-// stage caller input on the device if it is host memory
-int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
+// stage caller input on the device if it is host memory.  Only a rebuild (`match_prefetch`) may
+// consume a zb_grid_prefetch slot; zb_aabb / zb_layer_of / zb_slab_top_layer always copy.  A slot is
+// matched by (host pointer, n): the caller must leave the buffer untouched -- and alive -- between the
+// prefetch and the rebuild that consumes it (the contract of any asynchronous copy).  An armed slot
+// that two rebuilds in a row did not ask for is dropped, so a stale frame cannot wait forever for an
+// unrelated array that happens to reuse its address.
+int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev, bool match_prefetch = false) {
   const size_t bytes = (size_t)n * g->ndim * elem_size(g);
   if (n == 0) {
     *dev = nullptr;
@@ -484,13 +496,19 @@ int stage_input(zb_grid* g, const void* xyz, uint64_t n, const void** dev) {
     *dev = xyz;
     return ZB_OK;
   }
-  for (int k = 0; k < 2; ++k) {
-    auto& sl = g->pre[k];
-    if (sl.host == xyz && sl.n == n && sl.buf.p) {
+  if (match_prefetch) {
+    int hit = -1;
+    for (int k = 0; k < 2; ++k) {
+      auto& sl = g->pre[k];
+      if (hit < 0 && sl.host == xyz && sl.n == n && sl.buf.p) hit = k;
+      else if (sl.host && ++sl.age >= 2) sl.host = nullptr;  // nobody came for it
+    }
+    if (hit >= 0) {
+      auto& sl = g->pre[hit];
       // the copy was started by zb_grid_prefetch on the copy stream: wait for it on the device
       ZB_CUDA(cudaStreamWaitEvent(g->stream, sl.copied, 0));
       sl.host = nullptr;  // consumed (the slot stays reserved until `released` fires)
-      g->pre_in_use = k;
+      g->pre_in_use = hit;
       *dev = sl.buf.p;
       return ZB_OK;
     }
@@ -521,7 +539,7 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
     g->info_pending = false;
   }
   const void* dev = nullptr;
-  ZB_TRY(stage_input(g, xyz_any, n, &dev));
+  ZB_TRY(stage_input(g, xyz_any, n, &dev, true));
   const T* xyz = static_cast<const T*>(dev);
 
   const uint32_t* labels = nullptr;
@@ -645,13 +663,10 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   PairPlan pl;
   // f64 grids with a distance filter run staged tiles through the f32 prefilter (pair_kernels.cuh)
   // (opt-in: measured at parity with the exact loop on the benchmark box)
-  pl.prefilter = sizeof(T) == 8 && cmp != ZB_CMP_NONE && getenv("ZB_PREFILTER") != nullptr;
+  pl.prefilter = sizeof(T) == 8 && cmp != ZB_CMP_NONE && g->tune.prefilter;
   const size_t rec_bytes = sizeof(Rec<T>) + (pl.prefilter ? sizeof(float4) : 0);
   pl.stage_recs = sizeof(T) == 8 ? (pl.prefilter ? 1024u : 1408u) : 2816u;  // 44-48 KB of stage: 4 CTAs per SM
-  if (const char* e = getenv("ZB_STAGE_RECS")) {     // tuning knob for experiments
-    const long v = atol(e);
-    if (v >= 64 && v <= 6144) pl.stage_recs = (uint32_t)v;
-  }
+  if (g->tune.stage_recs) pl.stage_recs = g->tune.stage_recs;
   const uint64_t plane = (g->ndim == 3) ? (uint64_t)g->wshape[0] * g->wshape[1] : 0;
   const uint64_t halo = plane + (uint64_t)g->wshape[0] + 1;
   const uint32_t nhome = g->home_hi - g->home_lo;
@@ -666,10 +681,7 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   // enough tiles to balance the persistent grid
   const uint32_t want_tiles = (uint32_t)g->sm_count * 4 * 4;
   if (nhome / std::max(tc, 1u) < want_tiles) tc = std::max<uint32_t>(8, (nhome + want_tiles - 1) / want_tiles);
-  if (const char* e = getenv("ZB_TILE_CELLS")) {     // tuning knob for experiments
-    const long v = atol(e);
-    if (v >= 1) tc = (uint32_t)v;
-  }
+  if (g->tune.tile_cells) tc = g->tune.tile_cells;
   tc = std::min<uint32_t>(std::max<uint32_t>(tc, 1), kMaxTileCells);
   pl.tile_cells = tc;
   pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
@@ -735,6 +747,8 @@ int sparse_tile_list(zb_grid* g, const PairPlan& pl, PairParams<T>& p) {
     ZB_CUDA(cudaGetLastError());
     g->tile_list_build = g->build_id;
     g->tile_list_cells = pl.tile_cells;
+    // the list is filled in atomic arrival order: per-work-item counts of an earlier list are void
+    g->emit_cache_valid = false;
   }
   p.tile_list = buf + 1;
   p.tile_list_n = buf;
@@ -891,6 +905,15 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   g->device = device;
   g->dtype = dtype;
   g->ndim = ndim;
+  if (const char* e = getenv("ZB_PREFILTER")) g->tune.prefilter = atoi(e) != 0;
+  if (const char* e = getenv("ZB_STAGE_RECS")) {
+    const long v = atol(e);
+    if (v >= 64 && v <= 6144) g->tune.stage_recs = (uint32_t)v;
+  }
+  if (const char* e = getenv("ZB_TILE_CELLS")) {
+    const long v = atol(e);
+    if (v >= 1) g->tune.tile_cells = (uint32_t)v;
+  }
   auto bail = [&](int rc) {
     zb_grid_destroy(g);
     return rc;
@@ -1007,6 +1030,7 @@ int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n) {
   ZB_CUDA(cudaEventRecord(sl.copied, g->copy_stream));
   sl.host = xyz_host;
   sl.n = n;
+  sl.age = 0;
   return ZB_OK;
 }
 
@@ -1571,6 +1595,12 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
   ZB_TRY(derive_shape<T>(g));
   const int ax = nd - 1;
   const int64_t nz = g->shape[ax];
+  // every rank must own at least one layer: the lower halo is taken from rank - 1's top layer only, a
+  // rank with an empty slab would cut the chain.  nz comes from the all-reduced box, so every rank takes
+  // this exit together and nobody is left waiting in a collective.
+  if (nz < N.world)
+    return fail(g, ZB_ERR_BAD_ARG, "the grid has %lld layers along the slab axis, fewer than the %d ranks", (long long)nz,
+                N.world);
   const int64_t z_begin = (int64_t)N.rank * nz / N.world, z_end = (int64_t)(N.rank + 1) * nz / N.world;
 
   // 2 + 3. sharded rebuild with the imposed box.  K2 over the local rows also extracts this slab's top
@@ -1655,20 +1685,30 @@ int zb_grid_rebuild_slab_local(zb_grid* g, void* buf, uint64_t n_local, uint64_t
 
 int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs) {
   ZB_TRY(enter(g));
-  ZB_TRY(check_built(g));
   auto& N = g->nccl;
   if (!N.comm) return fail(g, ZB_ERR_NOT_BUILT, "zb_comm_init has not been called");
   if (!energy) return fail(g, ZB_ERR_BAD_ARG, "energy is NULL");
   if (cmp < 1 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "lj energy needs a distance filter (cmp LT or LE)");
-  if (g->dtype == ZB_F32) ZB_TRY(lj_impl<float>(g, cmp, filter_cutoff));
-  else ZB_TRY(lj_impl<double>(g, cmp, filter_cutoff));
-  // (energy, pair count as f64: exact below 2^53) -> one all-reduce(sum) -> host
+  // A rank whose slab step failed (halo overflow, particle outside its layers, ...) still enters the
+  // collective -- with a raised error flag in the third slot -- so that its peers are not left hanging;
+  // every rank then reports the failure.
   double* red = static_cast<double*>(g->red.p);
-  pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, red);
-  g->launches++;
-  ZB_NCCL(N.AllReduce(red, red, 2, ncclDouble, ncclSum, N.comm, g->stream));
-  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 2 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  int local_rc = g->built ? ZB_OK : ZB_ERR_NOT_BUILT;
+  if (local_rc == ZB_OK) local_rc = g->dtype == ZB_F32 ? lj_impl<float>(g, cmp, filter_cutoff) : lj_impl<double>(g, cmp, filter_cutoff);
+  if (local_rc == ZB_OK) {
+    // (energy, pair count as f64: exact below 2^53, error flag) -> one all-reduce(sum) -> host
+    pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, red);
+    g->launches++;
+  } else {
+    const double bad[3] = {0.0, 0.0, 1.0};
+    ZB_CUDA(cudaMemcpyAsync(red, bad, sizeof bad, cudaMemcpyHostToDevice, g->stream));
+  }
+  ZB_NCCL(N.AllReduce(red, red, 3, ncclDouble, ncclSum, N.comm, g->stream));
+  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 3 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (local_rc != ZB_OK) return local_rc;  // g->err holds this rank's own reason
+  if (g->h_red[2] != 0.0)
+    return fail(g, ZB_ERR_NOT_BUILT, "%d rank(s) failed their slab step; the all-reduced energy is not valid", (int)g->h_red[2]);
   *energy = g->h_red[0];
   if (n_pairs) *n_pairs = (uint64_t)g->h_red[1];
   return ZB_OK;

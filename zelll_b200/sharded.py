@@ -302,6 +302,10 @@ class DistributedCellGrid:
             self.cutoff = float(self.dtype.type(cutoff))
             self.shape = grid_shape(self.inf, self.sup, cutoff, self.dtype)
             self.z_begin, self.z_end = slab_bounds(self.shape[-1], self.world, self.rank)
+        if self.shape[-1] < self.world:
+            # the lower halo comes from rank - 1's top layer only: an empty slab would cut the chain
+            # (the general all-to-all path, rebuild(), has no such limit)
+            raise ValueError(f"slab-local input needs at least one layer per rank: {self.shape[-1]} layers, {self.world} ranks")
         up, down = self.rank + 1, self.rank - 1
         if self._halo_send is None or self._halo_send.shape[0] != halo_cap + 1 or self._halo_send.device != buf.device:
             self._halo_send = torch.zeros((halo_cap + 1, 4), dtype=buf.dtype, device=buf.device)
