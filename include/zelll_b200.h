@@ -250,6 +250,9 @@ int zb_grid_profile_read(zb_grid* g, double* stage_ms, uint64_t* stage_launches)
 /* Number of kernel launches this handle has issued since creation (bench.py's gpu_launches). */
 uint64_t zb_grid_launch_count(const zb_grid* g);
 int zb_abi_version(void);
+/* SHA-256 (hex) of the sources this binary was compiled from (zelll_b200/csrc/ and this header, as
+ * hashed by zelll_b200/build.py): lets a test prove that the shipped, git-ignored .so matches the tracked sources. */
+const char* zb_build_id(void);
 
 #ifdef __cplusplus
 }

@@ -154,3 +154,11 @@ def test_header_is_valid_c_and_links(tmp_path, lib):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "abi 1" in out.stdout
+
+
+def test_build_is_hash_based():
+    """build() rebuilds when (and only when) the sources' hash differs from the id compiled into the .so."""
+    from zelll_b200 import build
+
+    build.build()
+    assert build.built_hash() == build.source_hash() and not build.stale()

@@ -4,6 +4,7 @@ reference's known answers, and -- at BASELINE.json's full size -- through size-i
 properties.  Bar: bit-exact for keys / cells / pair sets / counts; 1e-10 (f64) and 1e-5 (f32)
 relative for the Lennard-Jones energy."""
 import itertools
+import os
 import pickle
 
 import numpy as np
@@ -724,7 +725,7 @@ def test_stage_profile_mask_and_rebuild_mut_shrinking_box(zb):
     cg.rebuild_mut(pts, None)
     cg.lj_energy(cutoff, "lt")
     st = cg.profile_read()
-    assert st["pair_lj"][1] == 1 and st["pair_lj"][0] > 0
+    assert st["pair_lj"][1] in (1, 2) and st["pair_lj"][0] > 0  # f64: prefilter kernel + exact kernel over its work list
     assert all(v[1] == 0 for k, v in st.items() if k != "pair_lj")
     cg.profile(True)
     cg.rebuild_mut(pts, None)
@@ -738,3 +739,14 @@ def test_stage_profile_mask_and_rebuild_mut_shrinking_box(zb):
         assert cg.info().n_cells == og.info()["n_cells"]
         assert cg.pair_count(cutoff, "le") == og.pair_count(CMP_LE, cutoff)
         assert np.array_equal(canonical_pairs(cg.particle_pairs(cutoff, "lt")), og.pairs_canonical(CMP_LT, cutoff))
+
+
+def test_binary_matches_tracked_sources():
+    """The library under test is the one the tracked sources build (the .so is git-ignored and ships
+    prebuilt): zb_build_id() = SHA-256 of csrc/ + header + flags, as zelll_b200/build.py hashes them."""
+    from zelll_b200 import _ffi, build
+
+    if os.environ.get("ZB_LIB"):
+        pytest.skip("experiment build selected with ZB_LIB")
+    got = _ffi.load().zb_build_id().decode()
+    assert got == "zb-build-id:" + build.source_hash()

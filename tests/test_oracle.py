@@ -258,3 +258,24 @@ def test_reference_sdf_golden(golden):
         near = cg.query_neighbors(x, CMP_LE, g["cutoff"])
         d = np.sqrt(((pts - x) ** 2).sum(axis=1))
         assert sorted(near.tolist()) == np.nonzero(d <= g["cutoff"])[0].tolist()
+
+
+def test_cross_tool_inputs():
+    """the LAMMPS deck and CellListMap settings of the reference's comparison
+    (more_benches/in.zelllbench.txt:30-36, more_benches/celllistmap.jl:18-43) next to the data writer."""
+    deck = workload.lammps_input(10.0, repeat=5, data_file="atoms.txt")
+    for needle in ("units lj", "atom_style atomic", "boundary f f f", "read_data ${data} add merge",
+                   "pair_style lj/cut ${cutoff}", "pair_coeff 1 1 1.0 1.0", "neighbor 0.0 bin",
+                   "neigh_modify delay 0 every 1 check no one ${max_neighbors}", "run ${repeat}",
+                   "variable cutoff index 10.0", "variable repeat index 5", "variable data file atoms.txt"):
+        assert needle in deck, needle
+    cfg = workload.celllistmap_settings(100_000)
+    assert cfg["sides"] == [30.0, 30.0, 100_000 / 9.0] and cfg["cutoff"] == 10.0 and cfg["parallel"] is False
+    assert workload.celllistmap_settings(100)["sides"][2] == 30.0  # max(c, 3 cutoff), celllistmap.jl:31
+    script = workload.celllistmap_script(100_000)
+    assert "map_pairwise!" in script and "parallel=false" in script and "/ n" in script
+    # the data file those tools read: 10 header lines, then `id type x y z` rows (examples/lammps_data.rs:56-80)
+    pts = workload.generate_points_random(5)
+    text = workload.lammps_data(pts).splitlines()
+    assert text[2] == "5 atoms" and len(text) == 10 + 5 + 1
+    assert [float(v) for v in text[10].split()[2:]] == pts[0].tolist()

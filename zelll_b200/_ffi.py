@@ -55,6 +55,7 @@ _vp, _u64, _i64, _int, _dbl = C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_do
 _dp, _u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
 SIGNATURES = {
     "zb_abi_version": (_int, []),
+    "zb_build_id": (C.c_char_p, []),
     "zb_grid_create": (_int, [_int, _int, _int, C.POINTER(_vp)]),
     "zb_grid_destroy": (None, [_vp]),
     "zb_grid_set_stream": (_int, [_vp, _vp]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzelll_b200.so")
 SOURCES = ["zelll_b200.cu"]
-HEADERS = ["common.cuh", "build_kernels.cuh", "pair_kernels.cuh", "query_kernels.cuh"]
+HEADERS = ["common.cuh", "build_kernels.cuh", "pair_kernels.cuh", "pair_pf_kernels.cuh", "query_kernels.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -31,19 +31,42 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libzelll_b200.so")
 
 
-def stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+def source_hash() -> str:
+    """SHA-256 over the compiler flags and every source the library is built from (names and bytes, in
+    a fixed order).  Compiled in as zb_build_id(); tests compare the two, so a stale or foreign .so is
+    detected instead of being tested by accident."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "zelll_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    for d in deps:
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def built_hash() -> str:
+    """zb_build_id() of the library on disk ('' when it is missing or predates the symbol)."""
+    if not os.path.exists(LIB):
+        return ""
+    with open(LIB, "rb") as f:
+        blob = f.read()
+    k = blob.find(b"zb-build-id:")
+    return blob[k + 12:k + 12 + 64].decode("ascii", "replace") if k >= 0 else ""
+
+
+def stale() -> bool:
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, f'-DZB_BUILD_ID="zb-build-id:{source_hash()}"', "-o", LIB]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

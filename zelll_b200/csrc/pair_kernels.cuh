@@ -93,6 +93,13 @@ struct PairParams {
   const uint32_t* tile_list_n; // ... and their number (device memory)
   uint32_t* tile_next;         // dynamic tile claim: work items handed out beyond the first wave; 0 between launches
   uint32_t* tile_done;         // CTAs that finished; the last one out re-arms both counters
+  // prefilter kernel (pair_pf_kernels.cuh): work items it cannot take are appended here ...
+  uint32_t* fb_list;
+  uint32_t* fb_count;
+  // ... and the exact kernel, launched behind it, walks exactly those (nullptr: all work items).  Per-tile
+  // arrays stay indexed by the ORIGINAL work item.  The last CTA out clears the count for the next launch.
+  const uint32_t* work_list;
+  uint32_t* work_list_n;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -312,6 +319,7 @@ struct CountConsumer {
     unsigned long long* block_totals; // [gridDim.x]
   };
   static constexpr int kWarpSmemBytes = 0;
+  static constexpr int kPfWarpSmemBytes = 0;  // per-warp bytes under pf_pair_kernel
   static constexpr int kStage = 4;  // ZB_STAGE_PAIR_COUNT
   static constexpr bool kNeedLabels = false;
   static constexpr bool kCountsOnly = true;
@@ -393,6 +401,7 @@ struct EmitConsumer {
     uint2* out;
   };
   static constexpr int kWarpSmemBytes = (32 + 32 * kMaxNJ * 2) * sizeof(uint2);  // one row + one fused step
+  static constexpr int kPfWarpSmemBytes = 64 * sizeof(uint2);  // pf_pair_kernel hands over one row at a time
   static constexpr int kStage = 5;  // ZB_STAGE_PAIR_EMIT
   static constexpr bool kNeedLabels = true;
   static constexpr bool kCountsOnly = false;
@@ -458,6 +467,9 @@ struct EmitConsumer {
     }
     drain_exact_rows();
   }
+  // pair_pf_kernels.cuh: one exactly decided pair per lane; its rows are nearly full (only pairs inside
+  // the f32 guard band can fail), so they go straight to the tile's output range
+  __device__ __forceinline__ void hit(bool h, T, uint32_t li, uint32_t lj) { put(h, make_uint2(li, lj)); }
   template <int CMP, int NJ>
   __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&)[NJ], uint32_t ipos,
                                           const uint32_t (&jpos)[NJ]) {
@@ -510,6 +522,7 @@ struct LjConsumer {
   static constexpr int kExactBytes = (32 * kDrainRows + 32 * GenericNJ<T>::value * ZB_LJ_FUSE) * (int)sizeof(T);
   static constexpr int kPfBytes = sizeof(T) == 8 ? kQueueSlots * 4 : 0;
   static constexpr int kWarpSmemBytes = kExactBytes > kPfBytes ? kExactBytes : kPfBytes;
+  static constexpr int kPfWarpSmemBytes = 16;  // pf_pair_kernel evaluates rows in place (no dsq queue)
   static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
   static constexpr bool kNeedLabels = false;
   static constexpr bool kCountsOnly = false;
@@ -530,11 +543,12 @@ struct LjConsumer {
   bool pf;
   unsigned ltmask;
   double acc;
+  double acc4;             // pf_pair_kernel: sum of lj / 4
   unsigned long long cnt;  // per-lane pairs kept
 
   __device__ LjConsumer(const Args& args, ConsumerSmem*, void* warp_smem, T c2)
       : a(args), q(static_cast<T*>(warp_smem)), qn(0), q0(smem_u32(warp_smem)), qa(q0), pf(false),
-        ltmask(lanemask_lt()), acc(0.0), cnt(0) {
+        ltmask(lanemask_lt()), acc(0.0), acc4(0.0), cnt(0) {
     ex.rec = nullptr;
     ex.c2 = c2;
   }
@@ -613,6 +627,24 @@ struct LjConsumer {
       __syncwarp();
     }
   }
+  // pair_pf_kernels.cuh: one exactly decided pair per lane (h = it passed the filter), evaluated in place.
+  // acc4 collects t (t - 1) = lj / 4 with one fused multiply-add per pair; finish() scales by 4 (exact).
+  // The reciprocal is two Newton steps on the hardware seed (relative error ~1e-16 per pair; the energy
+  // tolerance of the north star is 1e-10 on the sum).
+  __device__ __forceinline__ void hit(bool h, T dsq, uint32_t, uint32_t) {
+    const double d = h ? (double)dsq : 1.0;  // idle lanes: a harmless finite value
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double t = (r * r) * r;
+    if (h) {
+      acc4 = __fma_rn(t, t - 1.0, acc4);
+      cnt += 1;
+    }
+  }
   __device__ __forceinline__ void add(uint32_t) {}
   __device__ __forceinline__ void chunk_end() {}
   template <int CMP>
@@ -631,6 +663,7 @@ struct LjConsumer {
     __shared__ double s_e[kPairWarps];
     __shared__ unsigned long long s_c[kPairWarps];
     if (!pf) drain_exact_leftovers();
+    acc += 4.0 * acc4;
     const double w = warp_reduce(acc, [](double x, double y) { return x + y; });
     const unsigned long long c = warp_reduce(cnt, [](unsigned long long x, unsigned long long y) { return x + y; });
     if (lane_id() == 0) {
@@ -890,15 +923,16 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
 
   const uint32_t plane = (uint32_t)p.w0 * (uint32_t)p.w1;
   const uint32_t halo = plane + (uint32_t)p.w0 + 1u;
-  const uint32_t nwork = p.tile_list ? __ldg(p.tile_list_n) : p.ntiles;
+  const uint32_t nwork = p.work_list ? *p.work_list_n : (p.tile_list ? __ldg(p.tile_list_n) : p.ntiles);
   // Work items are claimed DYNAMICALLY: the first wave statically (blockIdx.x), every further one
   // from a global counter, so that CTAs which drew cheap tiles take more of them (clustered
   // particle distributions; also the last, partial wave of a uniform box).  The claim is issued
   // at the start of a tile and read at its end, its round trip hides behind the tile's work;
   // s_tile is double-buffered so that the next claim cannot overwrite a value still being read.
   uint32_t par = 0;
-  for (uint32_t w = blockIdx.x; w < nwork;) {
+  for (uint32_t wi = blockIdx.x; wi < nwork;) {
     if (threadIdx.x == 0) s_tile[par] = gridDim.x + atomicAdd(p.tile_next, 1u);
+    const uint32_t w = p.work_list ? p.work_list[wi] : wi;  // plain loads: written by the launch before this one
     const uint32_t tile = p.tile_list ? __ldg(p.tile_list + w) : w;
     const uint32_t c0 = p.home_lo + tile * p.tile_cells;
     const uint32_t c1 = min(c0 + p.tile_cells, p.home_hi);
@@ -909,7 +943,7 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
     // sparse boxes: a tile without home particles has no pairs (its per-tile count stays 0)
     if (phi == __ldg(p.csr + c0)) {
       __syncthreads();
-      w = s_tile[par];
+      wi = s_tile[par];
       par ^= 1u;
       continue;
     }
@@ -991,7 +1025,7 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
       c = __shfl_sync(0xffffffffu, nxt, 0);
     }
     cons.template tile_end<CMP>(w);  // ends with __syncthreads(): the stage buffers may be overwritten
-    w = s_tile[par];
+    wi = s_tile[par];
     par ^= 1u;
   }
   cons.finish();
@@ -999,7 +1033,10 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
   // nobody will touch tile_next again (atomicInc wraps tile_done back to 0 by itself)
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicInc(p.tile_done, gridDim.x - 1) == gridDim.x - 1) *p.tile_next = 0u;
+    if (atomicInc(p.tile_done, gridDim.x - 1) == gridDim.x - 1) {
+      *p.tile_next = 0u;
+      if (p.work_list) *p.work_list_n = 0u;  // every CTA has read its bound: empty list for the next launch
+    }
   }
 }
 

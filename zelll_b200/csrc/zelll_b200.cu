@@ -26,6 +26,7 @@
 
 #include "build_kernels.cuh"
 #include "pair_kernels.cuh"
+#include "pair_pf_kernels.cuh"
 #include "query_kernels.cuh"
 
 using namespace zb;
@@ -65,8 +66,10 @@ struct Misc {
 
 struct PairPlan {
   uint32_t tile_cells, ntiles, stage_recs, blocks;
-  size_t smem;
-  bool prefilter;
+  size_t smem;        // dynamic shared memory of the kernel that runs first
+  bool prefilter;     // f64 grids: pf_pair_kernel first, then the exact kernel over the work items it declined
+  uint32_t stage_recs_exact;
+  size_t smem_exact;  // ... of that second launch
 };
 
 struct zb_grid {
@@ -120,6 +123,8 @@ struct zb_grid {
   DevBuf keys_old, keys_new;
   DevBuf tile_counts, tile_offsets, block_energy, block_totals;
   DevBuf out_stage; // staging for host-destination outputs
+  DevBuf pf_list;   // prefiltered pass: [count, work items...] left to the exact kernel
+  const void* pf_list_zeroed = nullptr;  // the allocation whose count has been cleared once
   DevBuf tile_list; // sparse boxes: [count, tile ids...] of the tiles with home particles
   uint64_t tile_list_build = ~0ull;  // build_id / tile_cells the list was made for
   uint32_t tile_list_cells = 0;
@@ -128,7 +133,7 @@ struct zb_grid {
   uint32_t pair_ntiles_cap = 0;
   // experiment knobs, read from the environment ONCE at zb_grid_create (never on the launch path)
   struct Tune {
-    bool prefilter = false;    // ZB_PREFILTER=1: f64 grids run staged tiles through the f32 prefilter
+    bool prefilter = true;     // ZB_PREFILTER=0: f64 grids use the exact-arithmetic kernel only
     uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
     uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
   } tune;
@@ -659,18 +664,27 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
 // pair kernels
 
 template <class T>
-PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
+PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, size_t pf_warp_smem, int cmp, double fc) {
   PairPlan pl;
-  // f64 grids with a distance filter run staged tiles through the f32 prefilter (pair_kernels.cuh)
-  // (opt-in: measured at parity with the exact loop on the benchmark box)
-  pl.prefilter = sizeof(T) == 8 && cmp != ZB_CMP_NONE && g->tune.prefilter;
-  const size_t rec_bytes = sizeof(Rec<T>) + (pl.prefilter ? sizeof(float4) : 0);
-  pl.stage_recs = sizeof(T) == 8 ? (pl.prefilter ? 1024u : 1408u) : 2816u;  // 44-48 KB of stage: 4 CTAs per SM
-  if (g->tune.stage_recs) pl.stage_recs = g->tune.stage_recs;
   const uint64_t plane = (g->ndim == 3) ? (uint64_t)g->wshape[0] * g->wshape[1] : 0;
   const uint64_t halo = plane + (uint64_t)g->wshape[0] + 1;
   const uint32_t nhome = g->home_hi - g->home_lo;
   const double ppc = g->ncells ? (double)g->n / (double)g->ncells : 0.0;
+  pl.stage_recs_exact = sizeof(T) == 8 ? 1408u : 2816u;  // 44 KB of stage: 3-4 CTAs per SM
+  if (g->tune.stage_recs) pl.stage_recs_exact = g->tune.stage_recs;
+  // f64 grids with a distance filter run through the f32 prefilter kernel (pair_pf_kernels.cuh) when a
+  // tile of the expected load fits its stage and the squared radius is an ordinary f32 number
+  pl.prefilter = false;
+  pl.stage_recs = pl.stage_recs_exact;
+  if (sizeof(T) == 8 && cmp != ZB_CMP_NONE && g->tune.prefilter) {
+    const double c2 = fc * fc;
+    const uint32_t sr = kPfStageRecs;
+    if (c2 > 1e-30 && c2 < 1e30 && halo + 9 < (uint64_t)kStageCells &&
+        (double)(halo + 9) * std::max(ppc, 0.25) <= 0.75 * sr) {
+      pl.prefilter = true;
+      pl.stage_recs = sr;
+    }
+  }
   uint32_t tc = 64;
   if (halo + 1 + 8 < (uint64_t)kStageCells) {
     // fill ~75 % of the stage with the expected load, bounded by the staged CSR window
@@ -685,9 +699,10 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, int cmp) {
   tc = std::min<uint32_t>(std::max<uint32_t>(tc, 1), kMaxTileCells);
   pl.tile_cells = tc;
   pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
-  pl.blocks = (uint32_t)g->sm_count * kMaxPairCtasPerSm;  // upper bound (buffers); the launch picks the real grid
-  pl.smem = (size_t)pl.stage_recs * rec_bytes + kMaxTileCells * sizeof(CellRuns) + (kStageCells + 4) * sizeof(uint32_t) +
-            kPairWarps * warp_smem;
+  pl.blocks = (uint32_t)g->sm_count * kMaxPairCtasPerSm * 2;  // upper bound (buffers): both launches of a prefiltered pass
+  pl.smem_exact = (size_t)pl.stage_recs_exact * sizeof(Rec<T>) + kMaxTileCells * sizeof(CellRuns) +
+                  (kStageCells + 4) * sizeof(uint32_t) + kPairWarps * warp_smem;
+  pl.smem = pl.prefilter ? pf_smem_bytes(pf_warp_smem) : pl.smem_exact;
   return pl;
 }
 
@@ -715,11 +730,15 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.tile_cells = pl.tile_cells;
   p.ntiles = pl.ntiles;
   p.stage_recs = pl.stage_recs;
+  p.fb_list = nullptr;
+  p.fb_count = nullptr;
+  p.work_list = nullptr;
+  p.work_list_n = nullptr;
   const T c = (T)filter_cutoff;
   p.c2 = c * c;  // cutoff.powi(2) in T (benches/lj.rs:85)
   p.fc = c;
   p.cell = (T)g->cutoff;
-  p.prefilter = pl.prefilter ? 1 : 0;
+  p.prefilter = 0;
   p.tile_list = nullptr;
   p.tile_list_n = nullptr;
   p.tile_next = &g->misc->pair_next;
@@ -755,42 +774,87 @@ int sparse_tile_list(zb_grid* g, const PairPlan& pl, PairParams<T>& p) {
   return ZB_OK;
 }
 
+// per-block output slots of the second launch of a prefiltered pass sit behind the first launch's
+template <class T>
+typename CountConsumer<T>::Args shift_args(typename CountConsumer<T>::Args a, uint32_t blocks, CountConsumer<T>*) {
+  a.block_totals += blocks;
+  return a;
+}
+template <class T>
+typename LjConsumer<T>::Args shift_args(typename LjConsumer<T>::Args a, uint32_t blocks, LjConsumer<T>*) {
+  a.block_energy += blocks;
+  a.block_totals += blocks;
+  return a;
+}
+template <class T>
+typename EmitConsumer<T>::Args shift_args(typename EmitConsumer<T>::Args a, uint32_t, EmitConsumer<T>*) {
+  return a;
+}
+
 template <class T, class Consumer>
 int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, typename Consumer::Args args) {
   PairParams<T> p = p_in;
   ZB_TRY(sparse_tile_list<T>(g, pl, p));
-  auto go = [&](auto kern) -> int {
+  auto go = [&](auto kern, size_t smem, const PairParams<T>& pp, typename Consumer::Args a, uint32_t* blocks_out) -> int {
     // persistent grid: one wave of resident CTAs.  The attribute / occupancy queries cost ~10 us of
     // host time, so their result is cached per (kernel, shared-memory size).
     int occ = 0;
     const void* key = reinterpret_cast<const void*>(kern);
     for (const auto& e : g->occ_cache)
-      if (e.kern == key && e.smem == pl.smem) occ = e.occ;
+      if (e.kern == key && e.smem == smem) occ = e.occ;
     if (occ == 0) {
-      ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPairThreads, pl.smem));
+      ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPairThreads, smem));
       occ = std::max(1, std::min(occ, (int)kMaxPairCtasPerSm));
-      g->occ_cache.push_back({key, pl.smem, occ});
+      g->occ_cache.push_back({key, smem, occ});
     }
-    pl.blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * (uint32_t)occ));
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * (uint32_t)occ));
     {
       StageSpan span(g, Consumer::kStage);
-      kern<<<pl.blocks, kPairThreads, pl.smem, g->stream>>>(p, args);
+      kern<<<blocks, kPairThreads, smem, g->stream>>>(pp, a);
     }
     g->launches++;
     ZB_CUDA(cudaGetLastError());
+    *blocks_out = blocks;
     return ZB_OK;
   };
+  auto exact = [&](const PairParams<T>& pp, size_t smem, typename Consumer::Args a, uint32_t* blocks_out) -> int {
+    switch (cmp) {
+      case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer, false>, smem, pp, a, blocks_out);
+      case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer, false>, smem, pp, a, blocks_out);
+      case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer, false>, smem, pp, a, blocks_out);
+    }
+    return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+  };
   if constexpr (sizeof(T) == 8) {
-    if (pl.prefilter && cmp == ZB_CMP_LT) return go(pair_kernel<T, 1, Consumer, true>);
-    if (pl.prefilter && cmp == ZB_CMP_LE) return go(pair_kernel<T, 2, Consumer, true>);
+    if (pl.prefilter && cmp != ZB_CMP_NONE) {
+      // 1. the f32-prefiltered kernel; work items it declines (oversized tiles, guard band too wide,
+      //    non-finite coordinates) go to a list ...
+      ZB_TRY(reserve(g, g->pf_list, ((size_t)pl.ntiles + 1) * 4));
+      if (g->pf_list_zeroed != g->pf_list.p) {
+        ZB_CUDA(cudaMemsetAsync(g->pf_list.p, 0, 4, g->stream));  // afterwards the exact kernel re-arms the count
+        g->pf_list_zeroed = g->pf_list.p;
+      }
+      uint32_t* fb = static_cast<uint32_t*>(g->pf_list.p);
+      p.fb_count = fb;
+      p.fb_list = fb + 1;
+      uint32_t b1 = 0, b2 = 0;
+      if (cmp == ZB_CMP_LT) ZB_TRY(go(pf_pair_kernel<1, Consumer>, pl.smem, p, args, &b1));
+      else ZB_TRY(go(pf_pair_kernel<2, Consumer>, pl.smem, p, args, &b1));
+      // 2. ... which the exact kernel walks; its per-block results sit behind the first launch's
+      PairParams<T> pe = p;
+      pe.stage_recs = pl.stage_recs_exact;
+      pe.work_list = fb + 1;
+      pe.work_list_n = fb;
+      ZB_TRY(exact(pe, pl.smem_exact, shift_args<T>(args, b1, static_cast<Consumer*>(nullptr)), &b2));
+      pl.blocks = b1 + b2;
+      return ZB_OK;
+    }
   }
-  switch (cmp) {
-    case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer, false>);
-    case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer, false>);
-    case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer, false>);
-  }
-  return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
+  uint32_t b = 0;
+  ZB_TRY(exact(p, pl.smem_exact, args, &b));
+  pl.blocks = b;
+  return ZB_OK;
 }
 
 int finalize(zb_grid* g, bool with_energy, uint32_t nblocks) {
@@ -804,7 +868,7 @@ int finalize(zb_grid* g, bool with_energy, uint32_t nblocks) {
 
 template <class T>
 int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* plan_out) {
-  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, cmp);
+  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, CountConsumer<T>::kPfWarpSmemBytes, cmp, fc);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   if (per_tile) ZB_TRY(reserve(g, g->tile_counts, ((size_t)pl.ntiles + 1) * 8));
   typename CountConsumer<T>::Args a;
@@ -821,7 +885,7 @@ int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* pla
 
 template <class T>
 int lj_impl(zb_grid* g, int cmp, double fc) {
-  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes, cmp);
+  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes, LjConsumer<T>::kPfWarpSmemBytes, cmp, fc);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   ZB_TRY(reserve(g, g->block_energy, (size_t)pl.blocks * 8));
   typename LjConsumer<T>::Args a;
@@ -850,7 +914,9 @@ int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev
   a.tile_offsets = static_cast<const unsigned long long*>(g->tile_offsets.p);
   a.out = out_dev;
   PairPlan pe = pl;
-  pe.smem = pl.smem - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
+  pe.smem = pl.prefilter ? pf_smem_bytes(EmitConsumer<T>::kPfWarpSmemBytes)
+                         : pl.smem - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
+  pe.smem_exact = pl.smem_exact - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
   if (pl.ntiles) ZB_TRY((launch_pairs<T, EmitConsumer<T>>(g, cmp, pe, pair_params<T>(g, pl, fc), a)));
   return ZB_OK;
 }
@@ -890,6 +956,11 @@ void free_buf(DevBuf& b) {
 extern "C" {
 
 int zb_abi_version(void) { return ZB_ABI_VERSION; }
+
+#ifndef ZB_BUILD_ID
+#define ZB_BUILD_ID "unknown"
+#endif
+const char* zb_build_id(void) { return ZB_BUILD_ID; }
 
 int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   if (!out) return ZB_ERR_BAD_ARG;
@@ -939,7 +1010,7 @@ void zb_grid_destroy(zb_grid* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
-                    &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->halo_send, &g->halo_recv, &g->halo_labels,
+                    &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->pf_list, &g->halo_send, &g->halo_recv, &g->halo_labels,
                     &g->red};
   for (DevBuf* b : bufs) free_buf(*b);
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);

@@ -90,3 +90,70 @@ def lammps_data(points: np.ndarray, vol=None, seed: int = REFERENCE_SEED) -> str
     lines += [f"{i + 1} 1 {fmt(p[0])} {fmt(p[1])} {fmt(p[2])}" for i, p in enumerate(pts)]
     lines.append("")
     return "\n".join(lines) + "\n"
+
+
+def lammps_input(cutoff: float = CUTOFF, repeat: int = 100, data_file: str = "atomsinabox.txt",
+                 max_neighbors: int = 100) -> str:
+    """LAMMPS input deck with the settings of the reference's cross-tool comparison
+    (more_benches/in.zelllbench.txt:5-38): reduced LJ units, atomic style, a NON-periodic box that
+    `read_data ... add merge` grows to the data file's extent, `pair_style lj/cut <cutoff>` with
+    epsilon = sigma = 1 (the dimensionless potential of benches/lj.rs:42-47), zero velocities, and a
+    binned neighbour list with zero skin that is rebuilt on every step (`neighbor 0.0 bin`,
+    `neigh_modify delay 0 every 1 check no`), i.e. one cell-list build + one energy pass per step --
+    the same work as one rebuild_mut + lj_energy here.  The thermo output's `PotEng` is the pair energy
+    PER ATOM: compare with lj_energy / n."""
+    lines = [
+        "# generated by zelll_b200.workload.lammps_input: LJ pair energy of the benchmark cloud",
+        f"# lmp -in <this file> -var data {data_file}",
+        f"variable cutoff index {float(cutoff)!r}",
+        f"variable repeat index {int(repeat)}",
+        f"variable data file {data_file}",
+        f"variable max_neighbors index {int(max_neighbors)}",
+        "units lj",
+        "atom_style atomic",
+        "boundary f f f",
+        "lattice none 1.0",
+        "region box block -0.1 0.1 -0.1 0.1 -0.1 0.1",
+        "create_box 1 box",
+        "read_data ${data} add merge",
+        "thermo_style yaml",
+        "mass 1 1.0",
+        "velocity all zero linear",
+        "pair_style lj/cut ${cutoff}",
+        "pair_coeff 1 1 1.0 1.0",
+        "neighbor 0.0 bin",
+        "neigh_modify delay 0 every 1 check no one ${max_neighbors}",
+        "run ${repeat}",
+    ]
+    return "\n".join(lines) + "\n"
+
+
+def celllistmap_settings(n: int, cutoff: float = CUTOFF) -> dict:
+    """The CellListMap.jl run of the reference's comparison (more_benches/celllistmap.jl:18-43) as data:
+    box sides (the benchmark box, the long side at least 3 cutoffs), cutoff, serial `map_pairwise!` over
+    lj(dsq) = 4 t (t - 1), t = (1 / dsq)^3, result divided by n (energy per atom, as LAMMPS prints it),
+    coordinates read from columns 3-5 of the LAMMPS data file after its 10 header lines."""
+    a, b, c = lj_box(n, cutoff)
+    return {
+        "package": "CellListMap.jl", "sides": [a, b, max(c, 3.0 * cutoff)], "cutoff": float(cutoff), "parallel": False,
+        "pair_function": "lj(dsq) = (t = (1 / dsq)^3; 4.0 * t * (t - 1.0))", "reduce": "sum / n",
+        "data_columns": [3, 4, 5], "data_skip_lines": 10,
+    }
+
+
+def celllistmap_script(n: int, cutoff: float = CUTOFF, data_file: str = "atomsinabox.txt") -> str:
+    """A Julia script that evaluates the same energy per atom with CellListMap.jl (settings above)."""
+    cfg = celllistmap_settings(n, cutoff)
+    sides = ", ".join(repr(float(v)) for v in cfg["sides"])
+    return "\n".join([
+        "# generated by zelll_b200.workload.celllistmap_script",
+        "using CSV, DataFrames, CellListMap",
+        f'df = DataFrame(CSV.File("{data_file}"; header=false, skipto={cfg["data_skip_lines"] + 1}, select={cfg["data_columns"]}))',
+        "xyz = permutedims(Matrix(df))",
+        "n = size(xyz, 2)",
+        "lj(dsq) = (t = (1 / dsq)^3; 4.0 * t * (t - 1.0))",
+        f"box = Box([{sides}], {float(cutoff)!r})",
+        "cl = CellList(xyz, box)",
+        f"e = map_pairwise!((x, y, i, j, dsq, acc) -> lj(dsq) + acc, 0.0, box, cl, parallel={str(cfg['parallel']).lower()}) / n",
+        'println(n, " ", e)',
+    ]) + "\n"
