@@ -188,28 +188,34 @@ __device__ __forceinline__ void pf_cell(const CellRuns& r, const PfStage& st, co
     uint32_t posl[NJ], lim[NJ];
 #pragma unroll
     for (int q = 0; q < NJ; ++q) {
-      const uint32_t k = kb + 32u * q + lane;
-      const bool valid = k < r.K;  // (slots q >= nj are idle for every lane)
-      posl[q] = r.pos(k) - st.plo;  // idle lane: the home cell's first record (in bounds)
-      // home particles [hbl, lim) pair with this candidate: all of them, or -- for a candidate that is the
-      // home cell's own particle -- the ones stored before it (intra-cell pairs once, iters.rs:29-36)
-      lim[q] = valid ? (k >= r.K - r.m ? posl[q] : hend) : hbl;
+      posl[q] = hbl;
+      lim[q] = hbl;  // idle slot: pairs with nothing
       float x = kPfIdle, y = kPfIdle, z = kPfIdle;
-      if (valid) {
-        const uint32_t a = st.xf + posl[q] * 4u;
-        x = lds_f32<0>(a);
-        y = lds_f32<kPfOffF>(a);
-        z = lds_f32<2 * kPfOffF>(a);
+      if (q < (int)nj) {  // warp-uniform
+        const uint32_t k = kb + 32u * q + lane;
+        const bool valid = k < r.K;
+        posl[q] = r.pos(k) - st.plo;  // idle lane: the home cell's first record (in bounds)
+        // home particles [hbl, lim) pair with this candidate: all of them, or -- for a candidate that is
+        // the home cell's own particle -- the ones stored before it (intra-cell pairs once, iters.rs:29-36)
+        lim[q] = valid ? (k >= r.K - r.m ? posl[q] : hend) : hbl;
+        if (valid) {
+          const uint32_t a = st.xf + posl[q] * 4u;
+          x = lds_f32<0>(a);
+          y = lds_f32<kPfOffF>(a);
+          z = lds_f32<2 * kPfOffF>(a);
+        }
       }
       cx[q] = pk2(x, x);
       cy[q] = pk2(y, y);
       cz[q] = pk2(z, z);
     }
-    // home particles in passes of up to 16 (8 aligned pairs); the first pass starts one record early when
-    // the cell starts at an odd index (that record's bit is masked out below)
+    // home particles in passes of up to kPass (aligned pairs; 16 so that two masks share a word, 32 for
+    // the count consumer); the first pass starts one record early when the cell starts at an odd index
+    // (that record's bit is masked out below)
+    constexpr uint32_t kPass = kCount ? 32u : 16u;
 #pragma unroll 1
-    for (uint32_t b0 = hbl & ~1u; b0 < hend; b0 += 16u) {
-      const uint32_t S = min(8u, (hend - b0 + 1u) >> 1);
+    for (uint32_t b0 = hbl & ~1u; b0 < hend; b0 += kPass) {
+      const uint32_t S = min(kPass / 2u, (hend - b0 + 1u) >> 1);
       uint32_t mask[NJ];
 #pragma unroll
       for (int q = 0; q < NJ; ++q) mask[q] = 0u;
@@ -221,17 +227,14 @@ __device__ __forceinline__ void pf_cell(const CellRuns& r, const PfStage& st, co
       // bit j of a mask belongs to home record top - j; keep records in [max(hbl, b0), lim)
       const uint32_t top = b0 + 2u * S - 1u;
       const uint32_t first = max(hbl, b0);
-      const uint32_t himask = (2u << (top - first)) - 1u;  // top - first <= 15
+      const uint32_t himask = top - first >= 31u ? 0xffffffffu : (2u << (top - first)) - 1u;
 #pragma unroll
       for (int q = 0; q < NJ; ++q) {
         const int32_t jlo = (int32_t)(top + 1u) - (int32_t)lim[q];
         mask[q] &= himask & shl_clamp(0xffffffffu, (uint32_t)max(jlo, 0));
       }
-      // two 32-bit words: bits [16 q', 16 q' + 16) of word w belong to candidate slot 2 w + q'
-      uint32_t w0 = mask[0] | (mask[1] << 16), w1 = mask[2] | (mask[3] << 16);
-      uint32_t c = __popc(w0) + __popc(w1);
-
       if constexpr (kCount) {
+        uint32_t c = (__popc(mask[0]) + __popc(mask[1])) + (__popc(mask[2]) + __popc(mask[3]));
         // some t of this lane inside the guard band (taken over ALL its tests, masked-out ones included:
         // conservative): decide the lane's pairs of this pass in f64
         const bool amb = tmin <= th.band;
@@ -258,6 +261,9 @@ __device__ __forceinline__ void pf_cell(const CellRuns& r, const PfStage& st, co
       } else {
         // every "maybe" is decided in f64.  Entries go to the warp's queue in LANE order (prefix sum of
         // the lanes' bit counts); full rows of 32 are evaluated with all lanes busy.
+        // two 32-bit words: bits [16 q', 16 q' + 16) of word w belong to candidate slot 2 w + q'
+        uint32_t w0 = mask[0] | (mask[1] << 16), w1 = mask[2] | (mask[3] << 16);
+        const uint32_t c = __popc(w0) + __popc(w1);
         const uint32_t total = __reduce_add_sync(0xffffffffu, c);
         if (total == 0) continue;
         const uint32_t e0 = top | (posl[0] << 16), e1 = top | (posl[1] << 16), e2 = top | (posl[2] << 16),

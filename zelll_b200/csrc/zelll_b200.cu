@@ -133,7 +133,11 @@ struct zb_grid {
   uint32_t pair_ntiles_cap = 0;
   // experiment knobs, read from the environment ONCE at zb_grid_create (never on the launch path)
   struct Tune {
-    bool prefilter = true;     // ZB_PREFILTER=0: f64 grids use the exact-arithmetic kernel only
+    // ZB_PREFILTER=<mask>: which consumers of an f64 grid run through the f32-prefiltered kernel
+    // (1 = count, 2 = LJ, 4 = pair list; 0 = exact-arithmetic kernel everywhere).  Default: count only --
+    // measured on B200 at n = 10^7: count 0.72 -> 0.6 ms, LJ 1.16 -> 1.43 ms, list 1.36 -> 2.06 ms
+    // (deciding every "maybe" in f64 costs what the cheaper tests save).
+    uint32_t prefilter = 1;
     uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
     uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
   } tune;
@@ -664,7 +668,7 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
 // pair kernels
 
 template <class T>
-PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, size_t pf_warp_smem, int cmp, double fc) {
+PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, size_t pf_warp_smem, int cmp, double fc, uint32_t pf_bit) {
   PairPlan pl;
   const uint64_t plane = (g->ndim == 3) ? (uint64_t)g->wshape[0] * g->wshape[1] : 0;
   const uint64_t halo = plane + (uint64_t)g->wshape[0] + 1;
@@ -676,7 +680,7 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, size_t pf_warp_smem, int
   // tile of the expected load fits its stage and the squared radius is an ordinary f32 number
   pl.prefilter = false;
   pl.stage_recs = pl.stage_recs_exact;
-  if (sizeof(T) == 8 && cmp != ZB_CMP_NONE && g->tune.prefilter) {
+  if (sizeof(T) == 8 && cmp != ZB_CMP_NONE && (g->tune.prefilter & pf_bit)) {
     const double c2 = fc * fc;
     const uint32_t sr = kPfStageRecs;
     if (c2 > 1e-30 && c2 < 1e30 && halo + 9 < (uint64_t)kStageCells &&
@@ -868,7 +872,8 @@ int finalize(zb_grid* g, bool with_energy, uint32_t nblocks) {
 
 template <class T>
 int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* plan_out) {
-  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, CountConsumer<T>::kPfWarpSmemBytes, cmp, fc);
+  // the sizing pass of zb_grid_pairs (per_tile) must tile exactly like the emit pass that follows it
+  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, CountConsumer<T>::kPfWarpSmemBytes, cmp, fc, per_tile ? 4u : 1u);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   if (per_tile) ZB_TRY(reserve(g, g->tile_counts, ((size_t)pl.ntiles + 1) * 8));
   typename CountConsumer<T>::Args a;
@@ -885,7 +890,7 @@ int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* pla
 
 template <class T>
 int lj_impl(zb_grid* g, int cmp, double fc) {
-  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes, LjConsumer<T>::kPfWarpSmemBytes, cmp, fc);
+  PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes, LjConsumer<T>::kPfWarpSmemBytes, cmp, fc, 2u);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   ZB_TRY(reserve(g, g->block_energy, (size_t)pl.blocks * 8));
   typename LjConsumer<T>::Args a;
@@ -976,7 +981,7 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   g->device = device;
   g->dtype = dtype;
   g->ndim = ndim;
-  if (const char* e = getenv("ZB_PREFILTER")) g->tune.prefilter = atoi(e) != 0;
+  if (const char* e = getenv("ZB_PREFILTER")) g->tune.prefilter = (uint32_t)atoi(e);
   if (const char* e = getenv("ZB_STAGE_RECS")) {
     const long v = atol(e);
     if (v >= 64 && v <= 6144) g->tune.stage_recs = (uint32_t)v;
