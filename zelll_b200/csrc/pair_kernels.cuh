@@ -32,13 +32,13 @@
 // Arithmetic.  dsq = (dx*dx + dy*dy) + dz*dz with separately rounded operations, exactly what
 // nalgebra::distance_squared does (benches/lj.rs:84); the TU is compiled with -fmad=false.
 //
-// f32 prefilter for f64 grids (OPT-IN, ZB_PREFILTER=1; measured at parity with the exact loop, which
-// is bound by instruction issue and the FP64 pipe together -- DESIGN.md section 6).  Staged tiles
-// also keep every record as float4 coordinates RELATIVE to the tile's first record; the test loop
-// runs in f32 (FFMA allowed) and classifies each pair against a guard band around the threshold
-// that is wider than the worst-case f32 error (derivation at prefilter_delta()).  Sure misses --
-// 80 % of the tests -- never touch the FP64 pipe; everything else is re-evaluated from the f64
-// records with the reference's exact arithmetic, so the pair set stays bit-exact.
+// f64 grids can also run through the f32-prefiltered kernel of pair_pf_kernels.cuh (same enumeration, tests
+// in packed f32 with a guard band, every "maybe" decided here-style in f64); work items that kernel declines
+// come back to pair_kernel through PairParams::work_list.
+//
+// MODE splits the kernel so that the hot variant stays small (instruction cache): 1 = staged tiles only
+// (tiles that do not fit the stage are appended to fb_list), 2 = global-memory tiles only (run over that
+// list by a second launch), 0 = both in one kernel.
 #pragma once
 
 #include "common.cuh"
@@ -60,7 +60,6 @@ constexpr int kMaxNJ = 4;  // candidates held in registers per lane (register ti
 #ifndef ZB_LJ_FUSE
 #define ZB_LJ_FUSE 2  // home particles per LJ compaction step (measured: 2 = 3 > 4 > 1)
 #endif
-constexpr int kQueueSlots = 32 + 32 * kMaxNJ;  // per-warp hit queue: one full row + one iteration's worth
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kStageCells = 512;  // staged CSR entries per tile (cells + halo + 1)
 constexpr int kMaxTileCells = 128;  // home cells per tile (their descriptors are staged)
@@ -87,7 +86,6 @@ struct PairParams {
   T c2;                 // squared filter radius, in T (cutoff.powi(2))
   T fc;                 // filter radius
   T cell;               // edge length of a grid cell (the grid's cutoff)
-  int prefilter;        // f64 only: run staged tiles through the f32 prefilter
   FastDiv div0, div1;   // division by w0 and by w1
   const uint32_t* tile_list;   // sparse boxes: ids of the tiles that hold home particles, else nullptr
   const uint32_t* tile_list_n; // ... and their number (device memory)
@@ -296,19 +294,12 @@ __device__ __forceinline__ float prefilter_delta(float R_over_fc) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Consumers.  test_n() (exact loop) / maybe_n() (prefilter loop) are called by all 32 lanes of a
-// warp in convergence, once per home particle with the NJ candidates a lane holds.
+// Consumers.  test_n() is called by all 32 lanes of a warp in convergence, once per (fused) home particle
+// step with the candidates a lane holds; hit() is the hand-over point of pf_pair_kernel.
 
 struct ConsumerSmem {
   unsigned long long tile_count;  // CountConsumer
   uint32_t cursor;                // EmitConsumer
-};
-
-// what the prefilter path needs to re-evaluate a pair exactly: staged records by tile-local position
-template <class T>
-struct ExactCtx {
-  const Rec<T>* rec;
-  T c2;
 };
 
 // -- count -----------------------------------------------------------------------------------
@@ -328,19 +319,14 @@ struct CountConsumer {
   static constexpr int kFuse = 1;              // home particles handed to test_n per call
   Args a;
   ConsumerSmem* cs;
-  ExactCtx<T> ex;
   uint32_t c32;              // per-lane, current chunk (one predicated add per test)
   unsigned long long cnt;    // per-lane, current tile
   unsigned long long total;  // thread 0: this block's running total
 
-  __device__ CountConsumer(const Args& args, ConsumerSmem* s, void*, T c2) : a(args), cs(s), c32(0), cnt(0), total(0) {
-    ex.rec = nullptr;
-    ex.c2 = c2;
-  }
-  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>* staged, bool) {
+  __device__ CountConsumer(const Args& args, ConsumerSmem* s, void*, T) : a(args), cs(s), c32(0), cnt(0), total(0) {}
+  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>*, bool) {
     if (threadIdx.x == 0) cs->tile_count = 0;
     cnt = 0;
-    ex.rec = staged;
   }
   template <int NJ>
   __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], const uint32_t (&)[NJ],
@@ -349,26 +335,6 @@ struct CountConsumer {
 #pragma unroll
     for (int q = 0; q < NJ; ++q)
       asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c32) : "r"((uint32_t)h[q]));
-  }
-  // prefilter: sure hits are counted at once; the rare in-band pair is decided in f64 on the spot
-  template <int CMP, int NJ>
-  __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&sure)[NJ], uint32_t ipos,
-                                          const uint32_t (&jpos)[NJ]) {
-    bool amb = false;
-#pragma unroll
-    for (int q = 0; q < NJ; ++q) {
-      c32 += sure[q] ? 1u : 0u;
-      amb = amb || (maybe[q] && !sure[q]);
-    }
-    if (__any_sync(0xffffffffu, amb)) {
-#pragma unroll
-      for (int q = 0; q < NJ; ++q)
-        if (maybe[q] && !sure[q]) {
-          uint32_t la, lb;
-          const T d = exact_dsq<T, false>(ex.rec + ipos, ex.rec + jpos[q], la, lb);
-          c32 += passes<CMP>(d, ex.c2) ? 1u : 0u;
-        }
-    }
   }
   __device__ __forceinline__ void add(uint32_t k) { cnt += k; }  // unfiltered candidates, no loop
   __device__ __forceinline__ void chunk_end() {
@@ -410,24 +376,17 @@ struct EmitConsumer {
   static constexpr int kMinBlocks = ZB_PAIR_MINBLOCKS;
   Args a;
   ConsumerSmem* cs;
-  ExactCtx<T> ex;
-  uint2* q;        // exact loop: (label, label) rows; prefilter loop: packed (ipos << 16 | jpos) in .x
+  uint2* q;        // (label, label) rows waiting for a full 32-row store
   uint32_t qn;
-  bool pf;
   unsigned ltmask;
   unsigned long long base;
 
-  __device__ EmitConsumer(const Args& args, ConsumerSmem* s, void* warp_smem, T c2)
-      : a(args), cs(s), q(static_cast<uint2*>(warp_smem)), qn(0), pf(false), ltmask(lanemask_lt()), base(0) {
-    ex.rec = nullptr;
-    ex.c2 = c2;
-  }
-  __device__ __forceinline__ void tile_begin(uint32_t tile, const Rec<T>* staged, bool prefilter) {
+  __device__ EmitConsumer(const Args& args, ConsumerSmem* s, void* warp_smem, T)
+      : a(args), cs(s), q(static_cast<uint2*>(warp_smem)), qn(0), ltmask(lanemask_lt()), base(0) {}
+  __device__ __forceinline__ void tile_begin(uint32_t tile, const Rec<T>*, bool) {
     if (threadIdx.x == 0) cs->cursor = 0;
     base = a.tile_offsets[tile];
     qn = 0;
-    ex.rec = staged;
-    pf = prefilter;
   }
   // write the rows for which `h` holds to the tile's output range
   __device__ __forceinline__ void put(bool h, uint2 row) {
@@ -446,16 +405,6 @@ struct EmitConsumer {
       __syncwarp();
     }
   }
-  template <int CMP>
-  __device__ __forceinline__ void drain_pf_row(bool valid, uint32_t entry) {
-    uint32_t la = 0, lb = 0;
-    bool h = false;
-    if (valid) {
-      const T d = exact_dsq<T, true>(ex.rec + (entry >> 16), ex.rec + (entry & 0xffffu), la, lb);
-      h = passes<CMP>(d, ex.c2);
-    }
-    put(h, make_uint2(la, lb));
-  }
   template <int NJ>
   __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&)[NJ], const uint32_t (&li)[NJ],
                                          const uint32_t (&lj)[NJ]) {
@@ -470,30 +419,13 @@ struct EmitConsumer {
   // pair_pf_kernels.cuh: one exactly decided pair per lane; its rows are nearly full (only pairs inside
   // the f32 guard band can fail), so they go straight to the tile's output range
   __device__ __forceinline__ void hit(bool h, T, uint32_t li, uint32_t lj) { put(h, make_uint2(li, lj)); }
-  template <int CMP, int NJ>
-  __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&)[NJ], uint32_t ipos,
-                                          const uint32_t (&jpos)[NJ]) {
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      const unsigned b = __ballot_sync(0xffffffffu, maybe[k]);
-      if (maybe[k]) q[qn + __popc(b & ltmask)].x = (ipos << 16) | jpos[k];
-      qn += __popc(b);
-    }
-    while (qn >= 32) {
-      __syncwarp();
-      qn -= 32;
-      drain_pf_row<CMP>(true, q[qn + lane_id()].x);
-      __syncwarp();
-    }
-  }
   __device__ __forceinline__ void add(uint32_t) {}
   __device__ __forceinline__ void chunk_end() {}
   template <int CMP>
   __device__ __forceinline__ void tile_end(uint32_t) {
     __syncwarp();
     if (qn > 0) {
-      if (pf) drain_pf_row<CMP>(lane_id() < qn, lane_id() < qn ? q[lane_id()].x : 0u);
-      else put(lane_id() < qn, q[lane_id() < qn ? lane_id() : 0]);
+      put(lane_id() < qn, q[lane_id() < qn ? lane_id() : 0]);
       qn = 0;
     }
     __syncthreads();
@@ -514,14 +446,13 @@ struct LjConsumer {
     double* block_energy;               // [gridDim.x]
     unsigned long long* block_totals;   // [gridDim.x]
   };
-  // exact loop: (32 + 32 NJ) dsq values; prefilter loop (f64 only): kQueueSlots packed positions
+  // (32 rows + one fused step) dsq values per warp
 #ifndef ZB_LJ_DRAIN_ROWS
 #define ZB_LJ_DRAIN_ROWS 2
 #endif
   static constexpr int kDrainRows = ZB_LJ_DRAIN_ROWS;
   static constexpr int kExactBytes = (32 * kDrainRows + 32 * GenericNJ<T>::value * ZB_LJ_FUSE) * (int)sizeof(T);
-  static constexpr int kPfBytes = sizeof(T) == 8 ? kQueueSlots * 4 : 0;
-  static constexpr int kWarpSmemBytes = kExactBytes > kPfBytes ? kExactBytes : kPfBytes;
+  static constexpr int kWarpSmemBytes = kExactBytes;
   static constexpr int kPfWarpSmemBytes = 16;  // pf_pair_kernel evaluates rows in place (no dsq queue)
   static constexpr int kStage = 6;  // ZB_STAGE_PAIR_LJ
   static constexpr bool kNeedLabels = false;
@@ -535,24 +466,15 @@ struct LjConsumer {
   // that overlap, and the queue bookkeeping / drain check is paid once for both
   static constexpr int kFuse = ZB_LJ_FUSE;
   Args a;
-  ExactCtx<T> ex;
-  T* q;          // exact loop: dsq; prefilter loop: uint32 (ipos << 16 | jpos) in the same bytes
-  uint32_t qn;   // prefilter loop: warp-uniform fill level (entries)
-  uint32_t q0;   // exact loop: shared-space byte address of q ...
+  uint32_t q0;   // shared-space byte address of this warp's queue of dsq values ...
   uint32_t qa;   // ... and of its fill position (warp-uniform)
-  bool pf;
   unsigned ltmask;
   double acc;
   double acc4;             // pf_pair_kernel: sum of lj / 4
   unsigned long long cnt;  // per-lane pairs kept
 
   __device__ LjConsumer(const Args& args, ConsumerSmem*, void* warp_smem, T c2)
-      : a(args), q(static_cast<T*>(warp_smem)), qn(0), q0(smem_u32(warp_smem)), qa(q0), pf(false),
-        ltmask(lanemask_lt()), acc(0.0), acc4(0.0), cnt(0) {
-    ex.rec = nullptr;
-    ex.c2 = c2;
-  }
-  __device__ __forceinline__ uint32_t* q32() { return reinterpret_cast<uint32_t*>(q); }
+      : a(args), q0(smem_u32(warp_smem)), qa(q0), ltmask(lanemask_lt()), acc(0.0), acc4(0.0), cnt(0) {}
   // what the exact loop left in the queue (< kDrainRows rows of dsq values)
   __device__ __forceinline__ void drain_exact_leftovers() {
     __syncwarp();
@@ -566,23 +488,7 @@ struct LjConsumer {
     qa = q0;
     __syncwarp();
   }
-  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>* staged, bool prefilter) {
-    if (prefilter && !pf) drain_exact_leftovers();  // the prefilter queue aliases the same bytes
-    ex.rec = staged;
-    pf = prefilter;
-  }
-  template <int CMP>
-  __device__ __forceinline__ void drain_pf_row(bool valid, uint32_t entry) {
-    uint32_t la, lb;
-    // idle lanes evaluate pair (0, 0) harmlessly: dsq = 0 never reaches the sum
-    const T d = exact_dsq<T, false>(ex.rec + (entry >> 16), ex.rec + (entry & 0xffffu), la, lb);
-    const bool h = valid && passes<CMP>(d, ex.c2);
-    const T e = lj_term(d);
-    if (h) {
-      acc += (double)e;
-      cnt += 1;
-    }
-  }
+  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>*, bool) {}
   template <int NJ>
   __device__ __forceinline__ void test_n(const bool (&h)[NJ], const T (&dsq)[NJ], const uint32_t (&)[NJ],
                                          const uint32_t (&)[NJ]) {
@@ -611,22 +517,6 @@ struct LjConsumer {
       __syncwarp();
     }
   }
-  template <int CMP, int NJ>
-  __device__ __forceinline__ void maybe_n(const bool (&maybe)[NJ], const bool (&)[NJ], uint32_t ipos,
-                                          const uint32_t (&jpos)[NJ]) {
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      const unsigned b = __ballot_sync(0xffffffffu, maybe[k]);
-      if (maybe[k]) q32()[qn + __popc(b & ltmask)] = (ipos << 16) | jpos[k];
-      qn += __popc(b);
-    }
-    while (qn >= 32) {
-      __syncwarp();
-      qn -= 32;
-      drain_pf_row<CMP>(true, q32()[qn + lane_id()]);
-      __syncwarp();
-    }
-  }
   // pair_pf_kernels.cuh: one exactly decided pair per lane (h = it passed the filter), evaluated in place.
   // acc4 collects t (t - 1) = lj / 4 with one fused multiply-add per pair; finish() scales by 4 (exact).
   // The reciprocal is two Newton steps on the hardware seed (relative error ~1e-16 per pair; the energy
@@ -649,20 +539,13 @@ struct LjConsumer {
   __device__ __forceinline__ void chunk_end() {}
   template <int CMP>
   __device__ __forceinline__ void tile_end(uint32_t) {
-    // prefilter queue entries refer to this tile's stage: empty it before the stage is reused
-    // (the exact loop queues dsq values, which stay valid: they wait for finish())
-    __syncwarp();
-    if (pf && qn > 0) {
-      const bool v = lane_id() < qn;
-      drain_pf_row<CMP>(v, v ? q32()[lane_id()] : 0u);
-      qn = 0;
-    }
+    // (the queue holds dsq values, which stay valid across tiles: they wait for finish())
     __syncthreads();
   }
   __device__ __forceinline__ void finish() {
     __shared__ double s_e[kPairWarps];
     __shared__ unsigned long long s_c[kPairWarps];
-    if (!pf) drain_exact_leftovers();
+    drain_exact_leftovers();
     acc += 4.0 * acc4;
     const double w = warp_reduce(acc, [](double x, double y) { return x + y; });
     const unsigned long long c = warp_reduce(cnt, [](unsigned long long x, unsigned long long y) { return x + y; });
@@ -838,75 +721,14 @@ __device__ __forceinline__ void process_cell(const CellRuns& r, const Recs recb,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Prefilter loop (f64 grids, staged tiles): the same enumeration on the float4 tile-relative
-// coordinates rel[pos - plo]; `lo` / `hi` are the guard-band thresholds (prefilter_delta).
-template <int CMP, int NJ, class Consumer>
-__device__ __forceinline__ void prefilter_tests(const float4* __restrict__ home, uint32_t m, uint32_t hpos,
-                                                const float (&xj)[NJ], const float (&yj)[NJ],
-                                                const float (&zj)[NJ], const uint32_t (&jpos)[NJ],
-                                                const uint32_t (&thr)[NJ], float lo, float hi, Consumer& cons) {
-#pragma unroll 2
-  for (uint32_t i = 0; i < m; ++i) {
-    const float4 v = home[i];
-    bool maybe[NJ], sure[NJ];
-#pragma unroll
-    for (int q = 0; q < NJ; ++q) {
-      const float dx = v.x - xj[q], dy = v.y - yj[q], dz = v.z - zj[q];
-      const float dsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-      const bool in = i < thr[q];
-      maybe[q] = in && dsq <= hi;
-      sure[q] = in && dsq < lo;
-    }
-    cons.template maybe_n<CMP, NJ>(maybe, sure, hpos + i, jpos);
-  }
-}
-
-template <int CMP, class Consumer>
-__device__ __forceinline__ void process_cell_prefilter(const CellRuns& r, const float4* __restrict__ rel, uint32_t plo,
-                                                       float lo, float hi, Consumer& cons) {
-  if (r.m == 0) return;
-  const unsigned lane = lane_id();
-  const float4* home = rel + (r.hb - plo);
-  for (uint32_t kb = 0; kb < r.K; kb += 32 * kMaxNJ) {
-    float xj[kMaxNJ], yj[kMaxNJ], zj[kMaxNJ];
-    uint32_t jpos[kMaxNJ], thr[kMaxNJ];
-#pragma unroll
-    for (int q = 0; q < kMaxNJ; ++q) {
-      const uint32_t k = kb + 32u * q + lane;
-      thr[q] = r.thr(k);
-      jpos[q] = r.pos(k) - plo;
-      if (kb + 32u * q < r.K) {
-        const float4 v = rel[jpos[q]];
-        xj[q] = v.x; yj[q] = v.y; zj[q] = v.z;
-      }
-    }
-    const uint32_t nj = min((r.K - kb + 31u) >> 5, (uint32_t)kMaxNJ);
-    auto run = [&](auto tag) {
-      constexpr int NJ = decltype(tag)::value;
-      float x[NJ], y[NJ], z[NJ];
-      uint32_t jp[NJ], t[NJ];
-#pragma unroll
-      for (int q = 0; q < NJ; ++q) { x[q] = xj[q]; y[q] = yj[q]; z[q] = zj[q]; jp[q] = jpos[q]; t[q] = thr[q]; }
-      prefilter_tests<CMP, NJ>(home, r.m, r.hb - plo, x, y, z, jp, t, lo, hi, cons);
-    };
-    if (nj == 1) run(IntTag<1>());
-    else if (nj == 2) run(IntTag<2>());
-    else if (nj == 3) run(IntTag<3>());
-    else run(IntTag<4>());
-    cons.chunk_end();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-template <class T, int CMP, class Consumer, bool PF>
+template <class T, int CMP, class Consumer, int MODE>
 __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kernel(PairParams<T> p, typename Consumer::Args args) {
-  constexpr bool kCanPrefilter = PF && sizeof(T) == 8 && CMP != 0;
+  constexpr bool kStagedOnly = MODE == 1, kGlobalOnly = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Rec<T>* s_rec = reinterpret_cast<Rec<T>*>(smem_raw);
-  float4* s_rel = reinterpret_cast<float4*>(s_rec + p.stage_recs);  // f64 + prefilter only
-  CellRuns* s_desc = reinterpret_cast<CellRuns*>(s_rel + ((kCanPrefilter && p.prefilter) ? p.stage_recs : 0u));
+  CellRuns* s_desc = reinterpret_cast<CellRuns*>(s_rec + (kGlobalOnly ? 0u : p.stage_recs));
   uint32_t* s_csr = reinterpret_cast<uint32_t*>(s_desc + kMaxTileCells);
-  unsigned char* s_cons = reinterpret_cast<unsigned char*>(s_csr + kStageCells + 4);
+  unsigned char* s_cons = reinterpret_cast<unsigned char*>(s_csr + (kGlobalOnly ? 4 : kStageCells + 4));
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ ConsumerSmem s_cs;
   __shared__ uint32_t s_next;  // next unclaimed home cell of the tile (dynamic balance between warps)
@@ -917,7 +739,7 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
   const T c2 = keep_in_reg(p.c2);
   Consumer cons(args, &s_cs, s_cons + (size_t)warp * Consumer::kWarpSmemBytes, c2);
 
-  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  if (!kGlobalOnly && threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   uint32_t phase = 0;
 
@@ -940,33 +762,19 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
     const uint32_t ncsr = c1 - cl + 1;
     const uint32_t plo = __ldg(p.csr + cl), phi = __ldg(p.csr + c1);
     const uint32_t np = phi - plo;
-    // sparse boxes: a tile without home particles has no pairs (its per-tile count stays 0)
-    if (phi == __ldg(p.csr + c0)) {
+    const bool staged = !kGlobalOnly && np <= p.stage_recs && ncsr <= (uint32_t)kStageCells;
+    // sparse boxes: a tile without home particles has no pairs (its per-tile count stays 0).
+    // Staged-only kernel: a tile that does not fit the stage goes to the list of the global-memory launch.
+    const bool empty = phi == __ldg(p.csr + c0);
+    if (empty || (kStagedOnly && !staged)) {
+      if (kStagedOnly && !empty && threadIdx.x == 0) p.fb_list[atomicAdd(p.fb_count, 1u)] = w;
       __syncthreads();
       wi = s_tile[par];
       par ^= 1u;
       continue;
     }
-    const bool staged = np <= p.stage_recs && ncsr <= (uint32_t)kStageCells;
 
-    // prefilter thresholds of this tile (warp-uniform)
-    bool pf = false;
-    float lo = 0.f, hi = 0.f;
-    if (kCanPrefilter && p.prefilter && staged && np > 0) {
-      const uint32_t nt = c1 - cl;  // cells spanned by the stage
-      const uint32_t sx = min((uint32_t)p.w0, nt);
-      const uint32_t sy = min((uint32_t)p.w1, (nt + (uint32_t)p.w0 - 1) / (uint32_t)p.w0 + 1);
-      const uint32_t sz = min((uint32_t)p.w2, (nt + plane - 1) / plane + 1);
-      const float R = (float)max(sx, max(sy, sz)) * (float)p.cell * 1.0001f;
-      const float delta = prefilter_delta(R / (float)p.fc);
-      if (delta < 0.25f) {
-        pf = true;
-        lo = __fmul_rd(__double2float_rd((double)c2), 1.0f - delta);
-        hi = __fmul_ru(__double2float_ru((double)c2), 1.0f + delta);
-      }
-    }
-
-    cons.tile_begin(w, s_rec, pf);  // per-tile arrays are indexed by work item (= tile id unless sparse)
+    cons.tile_begin(w, s_rec, false);  // per-tile arrays are indexed by work item (= tile id unless sparse)
     if (threadIdx.x == 0) s_next = c0 + kPairWarps;
     if (staged) {
       if (threadIdx.x == 0 && np > 0) {
@@ -986,23 +794,9 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
         s_desc[k] = r;
       }
     }
-    if (staged) {
-      if (np > 0) {
-        mbar_wait(&s_bar, phase);
-        phase ^= 1u;
-      }
-      if constexpr (kCanPrefilter) {
-        if (pf) {
-          // tile-relative f32 coordinates; origin = the stage's first record
-          const double ox = s_rec[0].x, oy = s_rec[0].y, oz = s_rec[0].z;
-          for (uint32_t k = threadIdx.x; k < np; k += kPairThreads) {
-            double x, y, z;
-            uint32_t l;
-            load_part<false>(s_rec + k, x, y, z, l);
-            s_rel[k] = make_float4((float)(x - ox), (float)(y - oy), (float)(z - oz), 0.f);
-          }
-        }
-      }
+    if (staged && np > 0) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
     }
     __syncthreads();
     // the stage as a biased shared-space address, pinned in a register for the whole tile
@@ -1012,10 +806,10 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
     for (uint32_t c = c0 + warp; c < c1;) {
       const CellRuns r = s_desc[c - c0];
       // separate call sites so that the staged ones compile to shared-memory loads (LDS)
-      if constexpr (kCanPrefilter) {
-        if (pf) process_cell_prefilter<CMP>(r, s_rel, plo, lo, hi, cons);
-        else if (staged) process_cell<T, CMP>(r, srecs, c2, cons);
-        else process_cell<T, CMP>(r, GlobalRecs<T>{p.sorted}, c2, cons);
+      if constexpr (kStagedOnly) {
+        process_cell<T, CMP>(r, srecs, c2, cons);
+      } else if constexpr (kGlobalOnly) {
+        process_cell<T, CMP>(r, GlobalRecs<T>{p.sorted}, c2, cons);
       } else {
         if (staged) process_cell<T, CMP>(r, srecs, c2, cons);
         else process_cell<T, CMP>(r, GlobalRecs<T>{p.sorted}, c2, cons);

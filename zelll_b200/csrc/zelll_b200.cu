@@ -138,6 +138,10 @@ struct zb_grid {
     // measured on B200 at n = 10^7: count 0.72 -> 0.6 ms, LJ 1.16 -> 1.43 ms, list 1.36 -> 2.06 ms
     // (deciding every "maybe" in f64 costs what the cheaper tests save).
     uint32_t prefilter = 1;
+    // ZB_SPLIT=1: exact kernel as two launches, staged tiles (half the code size) then global-memory tiles.
+    // Measured neutral on B200 (LJ 1.159 unsplit vs 1.178 ms split at n = 10^7): the 5 k-instruction kernel
+    // is not instruction-cache bound, so one launch stays the default.
+    bool split = false;
     uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
     uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
   } tune;
@@ -742,7 +746,6 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.c2 = c * c;  // cutoff.powi(2) in T (benches/lj.rs:85)
   p.fc = c;
   p.cell = (T)g->cutoff;
-  p.prefilter = 0;
   p.tile_list = nullptr;
   p.tile_list_n = nullptr;
   p.tile_next = &g->misc->pair_next;
@@ -822,41 +825,64 @@ int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, t
     *blocks_out = blocks;
     return ZB_OK;
   };
-  auto exact = [&](const PairParams<T>& pp, size_t smem, typename Consumer::Args a, uint32_t* blocks_out) -> int {
-    switch (cmp) {
-      case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer, false>, smem, pp, a, blocks_out);
-      case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer, false>, smem, pp, a, blocks_out);
-      case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer, false>, smem, pp, a, blocks_out);
-    }
+  // the exact kernel in one of its three shapes: 0 = staged and global tiles in one kernel, 1 = staged tiles
+  // only (others go to the work list), 2 = global-memory tiles only
+  auto exact = [&](int mode, const PairParams<T>& pp, size_t smem, typename Consumer::Args a, uint32_t* blocks_out) -> int {
+#define ZB_GO(M)                                                                          \
+  switch (cmp) {                                                                          \
+    case ZB_CMP_NONE: return go(pair_kernel<T, 0, Consumer, M>, smem, pp, a, blocks_out); \
+    case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer, M>, smem, pp, a, blocks_out);   \
+    case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer, M>, smem, pp, a, blocks_out);   \
+  }
+    if (mode == 1) { ZB_GO(1) } else if (mode == 2) { ZB_GO(2) } else { ZB_GO(0) }
+#undef ZB_GO
     return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
   };
+  // the work list shared by the two launches of a split pass
+  auto work_list = [&](PairParams<T>& pp) -> int {
+    ZB_TRY(reserve(g, g->pf_list, ((size_t)pl.ntiles + 1) * 4));
+    if (g->pf_list_zeroed != g->pf_list.p) {
+      ZB_CUDA(cudaMemsetAsync(g->pf_list.p, 0, 4, g->stream));  // afterwards the second launch re-arms the count
+      g->pf_list_zeroed = g->pf_list.p;
+    }
+    uint32_t* fb = static_cast<uint32_t*>(g->pf_list.p);
+    pp.fb_count = fb;
+    pp.fb_list = fb + 1;
+    return ZB_OK;
+  };
+  const size_t smem_global = kMaxTileCells * sizeof(CellRuns) + 8 * sizeof(uint32_t) + kPairWarps * Consumer::kWarpSmemBytes;
   if constexpr (sizeof(T) == 8) {
     if (pl.prefilter && cmp != ZB_CMP_NONE) {
       // 1. the f32-prefiltered kernel; work items it declines (oversized tiles, guard band too wide,
       //    non-finite coordinates) go to a list ...
-      ZB_TRY(reserve(g, g->pf_list, ((size_t)pl.ntiles + 1) * 4));
-      if (g->pf_list_zeroed != g->pf_list.p) {
-        ZB_CUDA(cudaMemsetAsync(g->pf_list.p, 0, 4, g->stream));  // afterwards the exact kernel re-arms the count
-        g->pf_list_zeroed = g->pf_list.p;
-      }
-      uint32_t* fb = static_cast<uint32_t*>(g->pf_list.p);
-      p.fb_count = fb;
-      p.fb_list = fb + 1;
+      ZB_TRY(work_list(p));
       uint32_t b1 = 0, b2 = 0;
       if (cmp == ZB_CMP_LT) ZB_TRY(go(pf_pair_kernel<1, Consumer>, pl.smem, p, args, &b1));
       else ZB_TRY(go(pf_pair_kernel<2, Consumer>, pl.smem, p, args, &b1));
       // 2. ... which the exact kernel walks; its per-block results sit behind the first launch's
       PairParams<T> pe = p;
       pe.stage_recs = pl.stage_recs_exact;
-      pe.work_list = fb + 1;
-      pe.work_list_n = fb;
-      ZB_TRY(exact(pe, pl.smem_exact, shift_args<T>(args, b1, static_cast<Consumer*>(nullptr)), &b2));
+      pe.work_list = p.fb_list;
+      pe.work_list_n = p.fb_count;
+      ZB_TRY(exact(0, pe, pl.smem_exact, shift_args<T>(args, b1, static_cast<Consumer*>(nullptr)), &b2));
       pl.blocks = b1 + b2;
       return ZB_OK;
     }
   }
+  if (g->tune.split && cmp != ZB_CMP_NONE) {
+    // staged tiles first (the small, hot kernel), then the tiles that did not fit the stage from global memory
+    ZB_TRY(work_list(p));
+    uint32_t b1 = 0, b2 = 0;
+    ZB_TRY(exact(1, p, pl.smem_exact, args, &b1));
+    PairParams<T> pe = p;
+    pe.work_list = p.fb_list;
+    pe.work_list_n = p.fb_count;
+    ZB_TRY(exact(2, pe, smem_global, shift_args<T>(args, b1, static_cast<Consumer*>(nullptr)), &b2));
+    pl.blocks = b1 + b2;
+    return ZB_OK;
+  }
   uint32_t b = 0;
-  ZB_TRY(exact(p, pl.smem_exact, args, &b));
+  ZB_TRY(exact(0, p, pl.smem_exact, args, &b));
   pl.blocks = b;
   return ZB_OK;
 }
@@ -982,6 +1008,7 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   g->dtype = dtype;
   g->ndim = ndim;
   if (const char* e = getenv("ZB_PREFILTER")) g->tune.prefilter = (uint32_t)atoi(e);
+  if (const char* e = getenv("ZB_SPLIT")) g->tune.split = atoi(e) != 0;
   if (const char* e = getenv("ZB_STAGE_RECS")) {
     const long v = atol(e);
     if (v >= 64 && v <= 6144) g->tune.stage_recs = (uint32_t)v;
