@@ -529,13 +529,94 @@ def test_error_statuses(zb):
 
 
 def test_very_sparse_box(zb):
-    """zelll's home turf: few particles in a huge box (10^8 cells here, almost all empty).  The dense
-    cell table still gives the reference's pair set; empty tiles are skipped."""
+    """zelll's home turf: few particles in a huge box (10^8 cells here, almost all empty).  The build
+    switches to compact sorted cells (O(n) memory, sparse_kernels.cuh) and still gives the reference's
+    cells, pair set and energy."""
     rng = np.random.default_rng(7)
     blobs = np.array([[0.0, 0.0, 0.0], [450.0, 20.0, 460.0], [30.0, 440.0, 10.0]])
     pts = blobs[rng.integers(0, 3, 6000)] + rng.normal(0.0, 1.5, (6000, 3))
     cg, og = _check_against_oracle(zb, pts, 1.0, np.float64, 3)
     assert int(np.prod(cg.info().shape().astype(np.int64))) > 5e7
+
+
+def test_box_beyond_2_31_cells(zb):
+    """A box the dense table cannot index (round 1: ZB_ERR_GRID_TOO_LARGE): 4000 particles in clusters
+    spread over ~10^11 cells.  The reference handles it trivially (hash map of non-empty cells)."""
+    rng = np.random.default_rng(11)
+    blobs = rng.random((5, 3)) * 5000.0
+    blobs[0] = 0.0
+    blobs[1] = 5000.0
+    pts = blobs[rng.integers(0, 5, 4000)] + rng.normal(0.0, 1.2, (4000, 3))
+    cg = zb.CellGrid(pts, 1.0)
+    og = OracleCellGrid(pts, 1.0)
+    info, oinfo = cg.info(), og.info()
+    shape = info.shape().astype(np.int64)
+    assert int(np.prod(shape)) > 2**31
+    assert info.shape().tolist() == oinfo["shape"] and info.strides().tolist() == oinfo["strides"]
+    assert info.n_cells == oinfo["n_cells"]
+    assert np.array_equal(cg.keys(), og.keys())   # the reference's i32 flat keys WRAP in a box this large
+    # cells: the same (key, label set) groups (the wrapped keys are neither sorted nor unique)
+    keys, begin, count = cg.cells()
+    labels, xyz = cg.cell_storage()
+    okeys, obegin, olen = og.cells()
+    olabels, _ = og.cell_storage()
+    got_cells = sorted((int(k), tuple(sorted(labels[b:b + c].tolist()))) for k, b, c in zip(keys, begin, count))
+    want_cells = sorted((int(k), tuple(sorted(olabels[int(b):int(b + c)].tolist()))) for k, b, c in zip(okeys, obegin, olen))
+    assert got_cells == want_cells
+    assert np.array_equal(xyz, pts[labels])
+    for cmp in ("none", "lt", "le"):
+        want = og.pairs_canonical(OCMP[cmp], 1.0)
+        assert np.array_equal(canonical_pairs(cg.particle_pairs(1.0, cmp)), want), cmp
+        assert cg.pair_count(1.0, cmp) == len(want)
+    _, e64, m = og.lj_energy(CMP_LT, 1.0)
+    e, m_gpu = cg.lj_energy(1.0, "lt", return_pairs=True)
+    assert m_gpu == m and abs(e - e64) <= F64_RTOL * abs(e64)
+    # point queries go through the compact cells too
+    lo, hi = pts.min(0), pts.max(0)
+    queries = np.vstack([pts[:50], blobs + 0.3, lo + rng.random((50, 3)) * (hi - lo)])
+    for cmp in ("none", "le"):
+        offsets, valid, labels = cg.query_neighbors_batch(queries, 1.0, cmp)
+        for q in range(len(queries)):
+            want = og.query_neighbors(queries[q], OCMP[cmp], 1.0)
+            if want is None:
+                assert not valid[q]
+            else:
+                assert valid[q]
+                assert sorted(labels[int(offsets[q]):int(offsets[q + 1])].tolist()) == sorted(want.tolist())
+
+
+def test_compact_cell_build_forced():
+    """ZB_SPARSE=2 forces the compact-cell build on ordinary clouds (benchmark box, cube, clusters, dense
+    cells, 2-D, tiny inputs, f32): cells, pair sets, counts and energies must be the oracle's, and the
+    records of a cell come out in input order (the radix sort is stable), as CellStorage::push leaves them."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, sys
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+import oracle, zelll_b200
+import test_gpu_parity as t
+for dtype in (np.float64, np.float32):
+    for kind, n, nd in (("lj", 20000, 3), ("cube", 5000, 3), ("clusters", 3000, 3), ("dense", 3000, 3), ("plane", 4000, 3),
+                        ("cube", 3000, 2), ("dense", 2000, 2)):
+        pts, c = t._cloud(kind, n, dtype, nd)
+        cg, og = t._check_against_oracle(zelll_b200, pts, c, dtype, nd)
+        labels, _ = cg.cell_storage()
+        keys, begin, count = cg.cells()
+        for b, m in zip(begin[:300], count[:300]):
+            assert np.all(np.diff(labels[b:b + m].astype(np.int64)) > 0)   # input order inside a cell
+for n in (0, 1, 2, 3, 31, 32, 33, 257):
+    pts = np.random.default_rng(n).random((n, 3)) * 3.0
+    t._check_against_oracle(zelll_b200, pts, 1.0, np.float64, 3)
+print("sparse ok")
+""" % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, ZB_SPARSE="2")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "sparse ok" in out.stdout, out.stdout[-1500:] + out.stderr[-2500:]
 
 
 def test_gridcell_views_reference_counts(zb, golden):

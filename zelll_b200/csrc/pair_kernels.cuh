@@ -38,7 +38,7 @@
 //
 // MODE splits the kernel so that the hot variant stays small (instruction cache): 1 = staged tiles only
 // (tiles that do not fit the stage are appended to fb_list), 2 = global-memory tiles only (run over that
-// list by a second launch), 0 = both in one kernel.
+// list by a second launch), 0 = both in one kernel, 3 = compact cells of a sparse grid (sparse_kernels.cuh).
 #pragma once
 
 #include "common.cuh"
@@ -98,6 +98,9 @@ struct PairParams {
   // arrays stay indexed by the ORIGINAL work item.  The last CTA out clears the count for the next launch.
   const uint32_t* work_list;
   uint32_t* work_list_n;
+  // sparse grids (sparse_kernels.cuh; MODE 3): "cells" are the compact non-empty cells u in [0, nuniq),
+  // csr = ubegin, ukeys[u] = cx + w0 (cy + w1 cz) ascending; neighbour cells are found by binary search
+  const unsigned long long* ukeys;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -616,6 +619,52 @@ __device__ __forceinline__ bool cell_runs(const PairParams<T>& p, uint32_t c, co
   return true;
 }
 
+// the same descriptor for compact cell u of a sparse grid: each run is the record range of (up to) three
+// consecutive keys, found by binary search among the cells before u (all half-shell cells have smaller keys)
+__device__ __forceinline__ uint32_t lower_bound_ukeys(const unsigned long long* __restrict__ a, uint32_t hi,
+                                                      unsigned long long key) {
+  uint32_t lo = 0;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(a + mid) < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+template <class T>
+__device__ __forceinline__ bool cell_runs_sparse(const PairParams<T>& p, uint32_t u, CellRuns& r) {
+  const uint32_t hb = __ldg(p.csr + u), he = __ldg(p.csr + u + 1);
+  r.hb = hb;
+  r.m = he - hb;
+  r.K = r.o1 = r.o2 = r.o3 = r.o4 = 0;
+  r.shA = r.shB = r.shC = r.shD = r.shE = 0;
+  if (r.m == 0) return false;
+  const unsigned long long w0 = (unsigned long long)p.w0, w1 = (unsigned long long)p.w1;
+  const unsigned long long key = __ldg(p.ukeys + u);
+  const unsigned long long cx = key % w0, row = key / w0, cy = row % w1, cz = row / w1;
+  const unsigned long long xl = cx > 0 ? 1u : 0u, xr = (cx + 1 < w0) ? 1u : 0u;
+  // records of the cells with keys [k0, k1] among the compact cells before u
+  auto range = [&](unsigned long long k0, unsigned long long k1, uint32_t& s, uint32_t& l) {
+    const uint32_t lo = lower_bound_ukeys(p.ukeys, u, k0);
+    uint32_t up = lo;
+    while (up < u && up < lo + 3u && __ldg(p.ukeys + up) <= k1) ++up;
+    s = __ldg(p.csr + lo);
+    l = __ldg(p.csr + up) - s;
+  };
+  uint32_t sA = 0, lA = 0, sB = 0, lB = 0, sC = 0, lC = 0, sD = 0, lD = 0;
+  if (cz > 0) {
+    const unsigned long long kb = key - w0 * w1;  // same (cx, cy), plane below
+    if (cy > 0) range(kb - w0 - xl, kb - w0 + xr, sA, lA);
+    range(kb - xl, kb + xr, sB, lB);
+    if (cy + 1 < w1) range(kb + w0 - xl, kb + w0 + xr, sC, lC);
+  }
+  if (cy > 0) range(key - w0 - xl, key - w0 + xr, sD, lD);
+  const uint32_t sE = (xl && u > 0 && __ldg(p.ukeys + u - 1) == key - 1) ? __ldg(p.csr + u - 1) : hb, lE = he - sE;
+  r.o1 = lA; r.o2 = r.o1 + lB; r.o3 = r.o2 + lC; r.o4 = r.o3 + lD; r.K = r.o4 + lE;
+  r.shA = sA; r.shB = sB - r.o1; r.shC = sC - r.o2; r.shD = sD - r.o3; r.shE = sE - r.o4;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Exact loop: one warp enumerates the half-shell pairs of home cell c in the arithmetic of T.
 //   recb / csrb are biased bases (GlobalRecs / StagedRecs): recb.load(pos) is record `pos` of the cell-sorted array and
@@ -723,7 +772,8 @@ __device__ __forceinline__ void process_cell(const CellRuns& r, const Recs recb,
 // ---------------------------------------------------------------------------------------------
 template <class T, int CMP, class Consumer, int MODE>
 __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kernel(PairParams<T> p, typename Consumer::Args args) {
-  constexpr bool kStagedOnly = MODE == 1, kGlobalOnly = MODE == 2;
+  constexpr bool kSparse = MODE == 3;  // compact cells of a sparse grid: global-memory tiles, searched descriptors
+  constexpr bool kStagedOnly = MODE == 1, kGlobalOnly = MODE == 2 || kSparse;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Rec<T>* s_rec = reinterpret_cast<Rec<T>*>(smem_raw);
   CellRuns* s_desc = reinterpret_cast<CellRuns*>(s_rec + (kGlobalOnly ? 0u : p.stage_recs));
@@ -758,7 +808,7 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
     const uint32_t tile = p.tile_list ? __ldg(p.tile_list + w) : w;
     const uint32_t c0 = p.home_lo + tile * p.tile_cells;
     const uint32_t c1 = min(c0 + p.tile_cells, p.home_hi);
-    const uint32_t cl = c0 > halo ? c0 - halo : 0u;
+    const uint32_t cl = kSparse ? c0 : (c0 > halo ? c0 - halo : 0u);  // (sparse grids: no staged halo, `halo` may have wrapped)
     const uint32_t ncsr = c1 - cl + 1;
     const uint32_t plo = __ldg(p.csr + cl), phi = __ldg(p.csr + c1);
     const uint32_t np = phi - plo;
@@ -790,7 +840,8 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
       const uint32_t* csrb = staged ? s_csr - cl : p.csr;
       for (uint32_t k = threadIdx.x; k < c1 - c0; k += kPairThreads) {
         CellRuns r;
-        cell_runs(p, c0 + k, csrb, r);
+        if constexpr (kSparse) cell_runs_sparse(p, c0 + k, r);
+        else cell_runs(p, c0 + k, csrb, r);
         s_desc[k] = r;
       }
     }

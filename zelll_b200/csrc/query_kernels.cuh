@@ -8,6 +8,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "sparse_kernels.cuh"
 
 namespace zb {
 
@@ -18,11 +19,13 @@ struct QueryParams {
   const uint32_t* csr;
   T c2;
   int cmp;  // 0 none, 1 <, 2 <=
+  const unsigned long long* ukeys;  // sparse grids: compact cell keys (csr = ubegin), else nullptr
+  uint32_t nuniq;
 };
 
 // One warp per query point.  EMIT = false: counts[q] = number of neighbours, valid[q];
 // EMIT = true: labels[offsets[q] ...] filled (order inside a query unspecified, as upstream).
-template <class T, bool EMIT>
+template <class T, bool EMIT, bool SPARSE>
 __global__ void __launch_bounds__(256) query_kernel(QueryParams<T> p, const T* __restrict__ queries, uint32_t nq,
                                                     unsigned long long* __restrict__ counts_or_offsets,
                                                     uint8_t* __restrict__ valid, uint32_t* __restrict__ labels) {
@@ -53,8 +56,16 @@ __global__ void __launch_bounds__(256) query_kernel(QueryParams<T> p, const T* _
         // the three x-neighbours are consecutive cells: one contiguous record range
         const int xa = max(ci[0] - 1, 0), xb = min(ci[0] + 1, p.g.shape[0] - 1);
         if (xa > xb) continue;
-        const uint32_t row = (uint32_t)p.g.wshape[0] * ((uint32_t)cy + (uint32_t)p.g.wshape[1] * (uint32_t)cz);
-        const uint32_t b = __ldg(p.csr + row + xa), e = __ldg(p.csr + row + xb + 1);
+        uint32_t b, e;
+        if (SPARSE) {
+          const unsigned long long row = (unsigned long long)p.g.shape[0] *
+                                         ((unsigned long long)cy + (unsigned long long)p.g.shape[1] * (unsigned long long)cz);
+          sparse_range(p.ukeys, p.csr, p.nuniq, row + (unsigned long long)xa, row + (unsigned long long)xb, b, e);
+        } else {
+          const uint32_t row = (uint32_t)p.g.wshape[0] * ((uint32_t)cy + (uint32_t)p.g.wshape[1] * (uint32_t)cz);
+          b = __ldg(p.csr + row + xa);
+          e = __ldg(p.csr + row + xb + 1);
+        }
         for (uint32_t s = b; s < e; s += 32) {
           const uint32_t k = s + lane;
           bool h = k < e;

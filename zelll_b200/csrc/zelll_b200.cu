@@ -28,6 +28,7 @@
 #include "pair_kernels.cuh"
 #include "pair_pf_kernels.cuh"
 #include "query_kernels.cuh"
+#include "sparse_kernels.cuh"
 
 using namespace zb;
 
@@ -123,6 +124,10 @@ struct zb_grid {
   DevBuf keys_old, keys_new;
   DevBuf tile_counts, tile_offsets, block_energy, block_totals;
   DevBuf out_stage; // staging for host-destination outputs
+  // sparse grids (sparse_kernels.cuh): compact sorted cells instead of the dense table
+  bool sparse = false;
+  uint32_t nuniq = 0;
+  DevBuf skeys[2], sidx[2], shist, sflags, ukeys, ubegin;
   DevBuf pf_list;   // prefiltered pass: [count, work items...] left to the exact kernel
   const void* pf_list_zeroed = nullptr;  // the allocation whose count has been cleared once
   DevBuf tile_list; // sparse boxes: [count, tile ids...] of the tiles with home particles
@@ -144,6 +149,9 @@ struct zb_grid {
     bool split = false;
     uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
     uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
+    // ZB_SPARSE: 0 = never use the compact-cell build (boxes beyond 2^31 cells are refused, as in round 1),
+    // 2 = always use it (tests), default 1 = when the dense table would cost more than ~4x the records
+    int sparse = 1;
   } tune;
 
   // native multi-GPU step (zb_comm_*): NCCL entry points resolved at run time from the NCCL the
@@ -269,7 +277,9 @@ int is_device_ptr(const void* p) {
 
 size_t elem_size(const zb_grid* g) { return g->dtype == ZB_F32 ? 4 : 8; }
 
-uint32_t* csr_ptr(zb_grid* g) { return static_cast<uint32_t*>(g->table.p) + 3; }
+uint32_t* csr_ptr(zb_grid* g) {
+  return g->sparse ? static_cast<uint32_t*>(g->ubegin.p) : static_cast<uint32_t*>(g->table.p) + 3;
+}
 uint32_t* cursor_ptr(zb_grid* g) { return static_cast<uint32_t*>(g->table.p) + 4; }
 
 template <class T>
@@ -471,6 +481,77 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t& n, 
   return ZB_OK;
 }
 
+// exclusive in-place scan of a uint32 array with K3's kernel; *nonempty (misc) counts its non-zero entries
+int scan_u32(zb_grid* g, uint32_t* a, uint32_t m) {
+  const uint32_t ntile = (m + kScanTile - 1) / kScanTile;
+  ZB_TRY(reserve(g, g->scan_state, (size_t)ntile * sizeof(unsigned long long)));
+  ZB_CUDA(cudaMemsetAsync(g->scan_state.p, 0, (size_t)ntile * sizeof(unsigned long long), g->stream));
+  ZB_CUDA(cudaMemsetAsync(&g->misc->tile_counter, 0, 2 * sizeof(uint32_t), g->stream));  // tile_counter, nonempty
+  scan_kernel<<<ntile, kScanThreads, 0, g->stream>>>(a, m, static_cast<unsigned long long*>(g->scan_state.p),
+                                                     &g->misc->tile_counter, &g->misc->nonempty);
+  g->launches++;
+  ZB_CUDA(cudaGetLastError());
+  return ZB_OK;
+}
+
+// Sparse build (sparse_kernels.cuh): 64-bit cell keys -> radix sort -> compact sorted cells + CSR -> records.
+// O(n) memory whatever the box; `key_bits` = width of the largest key.  One host round trip (the number of
+// non-empty cells sizes the pair pass).
+template <class T>
+int build_sorted_sparse(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t n, int key_bits) {
+  const uint32_t nn = (uint32_t)n;
+  for (int k = 0; k < 2; ++k) {
+    ZB_TRY(reserve(g, g->skeys[k], (size_t)n * 8));
+    ZB_TRY(reserve(g, g->sidx[k], (size_t)n * 4));
+  }
+  const uint32_t nblk = (nn + kSortTile - 1) / kSortTile;
+  // the scan kernel writes whole 16-element groups: pad to its tile
+  ZB_TRY(reserve(g, g->shist, ((size_t)256 * nblk + kScanTile) * 4));
+  ZB_TRY(reserve(g, g->sflags, ((size_t)n + 1 + kScanTile) * 4));
+  ZB_TRY(reserve(g, g->ukeys, ((size_t)n + 1) * 8));
+  ZB_TRY(reserve(g, g->ubegin, ((size_t)n + 2) * 4));
+  ZB_TRY(reserve(g, g->sorted, ((size_t)n + 16) * sizeof(Rec<T>)));
+  ZB_CUDA(cudaMemsetAsync(&g->misc->flags, 0, sizeof(int), g->stream));
+  const GridParams<T> p = make_params<T>(g);
+  const uint32_t pblocks = (nn + 255) / 256;
+  auto* k0 = static_cast<unsigned long long*>(g->skeys[0].p);
+  auto* k1 = static_cast<unsigned long long*>(g->skeys[1].p);
+  auto* i0 = static_cast<uint32_t*>(g->sidx[0].p);
+  auto* i1 = static_cast<uint32_t*>(g->sidx[1].p);
+  if (g->ndim == 3) keys64_kernel<T, 3><<<pblocks, 256, 0, g->stream>>>(xyz, nn, p, k0, i0, &g->misc->flags);
+  else keys64_kernel<T, 2><<<pblocks, 256, 0, g->stream>>>(xyz, nn, p, k0, i0, &g->misc->flags);
+  g->launches++;
+  uint32_t* hist = static_cast<uint32_t*>(g->shist.p);
+  // (+1 bit: the all-ones key of an out-of-box particle must sort last -- it does in every pass that runs,
+  // and passes above key_bits see only zeros for real keys)
+  for (int shift = 0; shift < key_bits; shift += 8) {
+    radix_hist_kernel<<<nblk, kSortThreads, 0, g->stream>>>(k0, nn, shift, nblk, hist);
+    g->launches++;
+    ZB_TRY(scan_u32(g, hist, 256u * nblk));
+    radix_scatter_kernel<<<nblk, kSortThreads, 0, g->stream>>>(k0, i0, nn, shift, nblk, hist, k1, i1);
+    g->launches++;
+    std::swap(k0, k1);
+    std::swap(i0, i1);
+  }
+  uint32_t* flags = static_cast<uint32_t*>(g->sflags.p);
+  heads_kernel<<<(nn + 1 + 255) / 256, 256, 0, g->stream>>>(k0, nn, flags);
+  g->launches++;
+  ZB_TRY(scan_u32(g, flags, nn + 1));  // misc->nonempty = number of heads = non-empty cells
+  uniq_compact_kernel<<<pblocks, 256, 0, g->stream>>>(k0, flags, nn, static_cast<unsigned long long*>(g->ukeys.p),
+                                                     static_cast<uint32_t*>(g->ubegin.p));
+  Rec<T>* sorted = static_cast<Rec<T>*>(g->sorted.p);
+  if (g->ndim == 3) gather_kernel<T, 3><<<pblocks, 256, 0, g->stream>>>(xyz, i0, nn, labels, sorted);
+  else gather_kernel<T, 2><<<pblocks, 256, 0, g->stream>>>(xyz, i0, nn, labels, sorted);
+  g->launches += 2;
+  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->tile_counter, &g->misc->tile_counter, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (g->h_misc->flags & 1) return fail(g, ZB_ERR_BAD_ARG, "a particle has a non-finite coordinate");
+  g->nuniq = g->h_misc->nonempty;
+  return ZB_OK;
+}
+
 template <class T>
 int track_keys(zb_grid* g) {
   // FlatIndex::rebuild_mut's return value (flatindex.rs:140-152)
@@ -609,7 +690,31 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
     hook->top.first = (int)(z_begin - g->wlo[ax]);
     hook->top.top = (int)(z_end - 1 - g->wlo[ax]);
   }
-  ZB_TRY(build_sorted<T>(g, xyz, ls, n, hook));  // n grows by the halo rows the hook received
+  // Dense count table (4 B per cell of the box) or compact sorted cells (O(n) memory)?  The compact build
+  // takes over when the table would be out of proportion to the particles or beyond 2^31 cells -- the
+  // reference's hash map pays only for non-empty cells (README.md:21-22, src/cellgrid.rs:120).
+  g->sparse = false;
+  bool use_sparse = false;
+  int key_bits = 1;
+  if (!sharded && n > 0 && g->tune.sparse) {
+    unsigned __int128 nc = 1;
+    for (int d = 0; d < 3; ++d) nc *= (unsigned __int128)(uint64_t)g->wshape[d];
+    use_sparse = g->tune.sparse == 2 || nc > (unsigned __int128)kMaxDenseCells ||
+                 nc > (unsigned __int128)(32ull * n + (1ull << 22));
+    if (use_sparse) {
+      if (nc >= ((unsigned __int128)1 << 62))
+        return fail(g, ZB_ERR_GRID_TOO_LARGE, "bounding box / cutoff needs more than 2^62 cells (%d x %d x %d)", g->wshape[0],
+                    g->wshape[1], g->wshape[2]);
+      while (((unsigned __int128)1 << key_bits) <= nc) ++key_bits;  // real keys < 2^key_bits - 1
+    }
+  }
+  if (use_sparse) {
+    ZB_TRY(build_sorted_sparse<T>(g, xyz, ls, n, key_bits));
+    g->sparse = true;
+    g->ncells = g->nuniq;  // "cells" of the pair pass = the compact non-empty cells
+  } else {
+    ZB_TRY(build_sorted<T>(g, xyz, ls, n, hook));  // n grows by the halo rows the hook received
+  }
 
   // home-cell range of the pair kernels
   {
@@ -684,7 +789,7 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, size_t pf_warp_smem, int
   // tile of the expected load fits its stage and the squared radius is an ordinary f32 number
   pl.prefilter = false;
   pl.stage_recs = pl.stage_recs_exact;
-  if (sizeof(T) == 8 && cmp != ZB_CMP_NONE && (g->tune.prefilter & pf_bit)) {
+  if (sizeof(T) == 8 && cmp != ZB_CMP_NONE && (g->tune.prefilter & pf_bit) && !g->sparse) {
     const double c2 = fc * fc;
     const uint32_t sr = kPfStageRecs;
     if (c2 > 1e-30 && c2 < 1e30 && halo + 9 < (uint64_t)kStageCells &&
@@ -742,6 +847,7 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.fb_count = nullptr;
   p.work_list = nullptr;
   p.work_list_n = nullptr;
+  p.ukeys = g->sparse ? static_cast<const unsigned long long*>(g->ukeys.p) : nullptr;
   const T c = (T)filter_cutoff;
   p.c2 = c * c;  // cutoff.powi(2) in T (benches/lj.rs:85)
   p.fc = c;
@@ -834,7 +940,7 @@ int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, t
     case ZB_CMP_LT: return go(pair_kernel<T, 1, Consumer, M>, smem, pp, a, blocks_out);   \
     case ZB_CMP_LE: return go(pair_kernel<T, 2, Consumer, M>, smem, pp, a, blocks_out);   \
   }
-    if (mode == 1) { ZB_GO(1) } else if (mode == 2) { ZB_GO(2) } else { ZB_GO(0) }
+    if (mode == 1) { ZB_GO(1) } else if (mode == 2) { ZB_GO(2) } else if (mode == 3) { ZB_GO(3) } else { ZB_GO(0) }
 #undef ZB_GO
     return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
   };
@@ -851,6 +957,12 @@ int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, t
     return ZB_OK;
   };
   const size_t smem_global = kMaxTileCells * sizeof(CellRuns) + 8 * sizeof(uint32_t) + kPairWarps * Consumer::kWarpSmemBytes;
+  if (g->sparse) {  // compact cells: global-memory tiles with searched descriptors
+    uint32_t b = 0;
+    ZB_TRY(exact(3, p, smem_global, args, &b));
+    pl.blocks = b;
+    return ZB_OK;
+  }
   if constexpr (sizeof(T) == 8) {
     if (pl.prefilter && cmp != ZB_CMP_NONE) {
       // 1. the f32-prefiltered kernel; work items it declines (oversized tiles, guard band too wide,
@@ -1009,6 +1121,7 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   g->ndim = ndim;
   if (const char* e = getenv("ZB_PREFILTER")) g->tune.prefilter = (uint32_t)atoi(e);
   if (const char* e = getenv("ZB_SPLIT")) g->tune.split = atoi(e) != 0;
+  if (const char* e = getenv("ZB_SPARSE")) g->tune.sparse = atoi(e);
   if (const char* e = getenv("ZB_STAGE_RECS")) {
     const long v = atol(e);
     if (v >= 64 && v <= 6144) g->tune.stage_recs = (uint32_t)v;
@@ -1042,7 +1155,8 @@ void zb_grid_destroy(zb_grid* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
                     &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
-                    &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->pf_list, &g->halo_send, &g->halo_recv, &g->halo_labels,
+                    &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->pf_list, &g->skeys[0], &g->skeys[1], &g->sidx[0], &g->sidx[1], &g->shist, &g->sflags,
+                    &g->ukeys, &g->ubegin, &g->halo_send, &g->halo_recv, &g->halo_labels,
                     &g->red};
   for (DevBuf* b : bufs) free_buf(*b);
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
@@ -1366,6 +1480,22 @@ int zb_grid_cells(zb_grid* g, int32_t* keys, uint32_t* begin, uint32_t* count, u
   *n_out = g->n_cells_nonempty;
   if (cap < g->n_cells_nonempty) return fail(g, ZB_ERR_CAPACITY, "need room for %llu cells", (unsigned long long)*n_out);
   if (g->n_cells_nonempty == 0) return ZB_OK;
+  if (g->sparse) {  // the compact cells are already the answer
+    const uint64_t nu = g->nuniq;
+    ZB_TRY(reserve(g, g->out_stage, nu * 12 + 64));
+    int32_t* dk = static_cast<int32_t*>(g->out_stage.p);
+    uint32_t* db = reinterpret_cast<uint32_t*>(dk + nu);
+    uint32_t* dc = db + nu;
+    cells_sparse_kernel<<<(uint32_t)((nu + 255) / 256), 256, 0, g->stream>>>(
+        static_cast<const unsigned long long*>(g->ukeys.p), static_cast<const uint32_t*>(g->ubegin.p), (uint32_t)nu, g->shape[0],
+        g->shape[1], dk, db, dc);
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    if (keys) ZB_TRY(deliver(g, keys, dk, nu * 4));
+    if (begin) ZB_TRY(deliver(g, begin, db, nu * 4));
+    if (count) ZB_TRY(deliver(g, count, dc, nu * 4));
+    return ZB_OK;
+  }
   // flags -> exclusive scan (K3's scan kernel) -> ordered compaction, then one copy per array
   const uint64_t nc = g->n_cells_nonempty;
   const uint32_t ntile = (g->ncells + kScanTile - 1) / kScanTile;
@@ -1534,9 +1664,16 @@ int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cm
     const T c = (T)filter_cutoff;
     qp.c2 = c * c;
     qp.cmp = cmp;
+    qp.ukeys = g->sparse ? static_cast<const unsigned long long*>(g->ukeys.p) : nullptr;
+    qp.nuniq = g->nuniq;
     const T* q = static_cast<const T*>(dq);
-    if (!emit) query_kernel<T, false><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, nullptr);
-    else query_kernel<T, true><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, dl);
+    if (g->sparse) {
+      if (!emit) query_kernel<T, false, true><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, nullptr);
+      else query_kernel<T, true, true><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, dl);
+    } else {
+      if (!emit) query_kernel<T, false, false><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, nullptr);
+      else query_kernel<T, true, false><<<wblocks, 256, 0, g->stream>>>(qp, q, (uint32_t)nq, doff, dvalid, dl);
+    }
     g->launches++;
     ZB_CUDA(cudaGetLastError());
     return ZB_OK;
