@@ -464,7 +464,7 @@ def run_ours(args):
     alg_bytes = {  # ALGORITHMIC bytes per particle, f64 (SURVEY.md 8d / DESIGN.md section 4)
         "bbox": 24.0, "count": 24.0, "scan": 0.8, "scatter": 24.0 + 24.0 + 4.0, "pair_lj": 24.8,
     }
-    n_local = n_per + (int(dg.slab.n_halo) if distributed else 0)
+    n_local = int(engine.info().n) if distributed else n_per  # own rows + the halo rows counted on the device
     kernels = {}
     for name, (ms, cnt) in stages.items():
         if cnt and name in alg_bytes:

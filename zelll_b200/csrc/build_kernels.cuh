@@ -232,7 +232,11 @@ template <class T, int NDIM, bool TOP>
 __global__ void __launch_bounds__(kPointThreads) count_kernel(const T* __restrict__ xyz, uint32_t n,
                                                               GridParams<T> g,
                                                               uint32_t* __restrict__ counts,
-                                                              int* __restrict__ flags, TopLayerOut<T> tl) {
+                                                              int* __restrict__ flags, TopLayerOut<T> tl,
+                                                              const uint32_t* __restrict__ n_dev = nullptr) {
+  // n_dev (halo rows of the slab-local step): the number of valid rows lives on the device; n is the
+  // capacity the grid was sized for
+  if (n_dev) n = min(n, *n_dev);
   const uint32_t base = blockIdx.x * (kPointThreads * kPointIlp) + threadIdx.x;
   uint32_t c[kPointIlp];
 #pragma unroll
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(kPointThreads) count_kernel(const T* __restric
       c[k] = local_cell(g, x, y, z);
       if (TOP) {
         const int layer = cell_coord(NDIM == 3 ? z : y, g.inf[NDIM - 1], g.cutoff) - g.wlo[NDIM - 1];
-        if (layer < tl.first || layer > tl.top) *tl.bad = 1;
+        if (layer < tl.first || layer > tl.top) atomicOr(tl.bad, 1);
         top = layer == tl.top;
       }
     }
@@ -410,7 +414,10 @@ template <class T, int NDIM>
 __global__ void __launch_bounds__(kPointThreads) scatter_kernel(const T* __restrict__ xyz, LabelSrc labels,
                                                                 uint32_t n, GridParams<T> g,
                                                                 uint32_t* __restrict__ cursor,
-                                                                Rec<T>* __restrict__ sorted) {
+                                                                Rec<T>* __restrict__ sorted, uint32_t n_fixed = 0,
+                                                                const uint32_t* __restrict__ n_dev = nullptr) {
+  // slab-local step: rows [0, n_fixed) are the rank's own, *n_dev halo rows follow (n = capacity)
+  if (n_dev) n = min(n, n_fixed + *n_dev);
   const uint32_t base = blockIdx.x * (kPointThreads * kPointIlp) + threadIdx.x;
   T x[kPointIlp], y[kPointIlp], z[kPointIlp];
   uint32_t c[kPointIlp], lab[kPointIlp], pos[kPointIlp];
@@ -517,12 +524,29 @@ __global__ void widen6_kernel(const T* __restrict__ in6, double* __restrict__ ou
   }
 }
 
+// slab-local step run with LAST step's bounding box: does the all-reduced box (-inf, sup as doubles) still
+// equal it?  Bit 2 of *flag = no (every rank sees the same box, hence the same verdict).
+struct Box6 {
+  double v[6];
+};
+__global__ void spec_check_kernel(const double* __restrict__ red6, Box6 expect, uint32_t* __restrict__ flag) {
+  const int k = threadIdx.x;
+  if (k < 6 && !(red6[k] == expect.v[k])) atomicOr(flag, 4u);
+}
+
 // received halo block -> packed coordinates behind the local particles + their labels
+// (the launch is sized for cap rows; the received count stays on the device: *n_out = rows that were taken,
+// bit 1 of *flag = the sender's layer or the room behind the local rows was too small)
 template <class T, int NDIM>
 __global__ void halo_unpack_kernel(const T* __restrict__ rows, uint32_t cap, T* __restrict__ xyz_tail,
-                                   uint32_t* __restrict__ halo_labels) {
+                                   uint32_t* __restrict__ halo_labels, uint32_t* __restrict__ n_out = nullptr,
+                                   uint32_t* __restrict__ flag = nullptr) {
   const uint32_t n = (uint32_t)rows[0];
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0 && n_out) {
+    *n_out = min(n, cap);
+    if (n > cap) atomicOr(flag, 2u);
+  }
   if (r >= n || r >= cap) return;
   const T* row = rows + (uint64_t)(r + 1) * 4;
   xyz_tail[(uint64_t)r * NDIM] = row[0];
@@ -562,7 +586,7 @@ __global__ void __launch_bounds__(256) slab_top_kernel(const T* __restrict__ xyz
   if (i < n) {
     load_point<T, NDIM>(xyz, i, x, y, z);
     const int layer = cell_coord(NDIM == 3 ? z : y, inf, cutoff);
-    if (layer < z_begin || layer >= z_end) *bad = 1;
+    if (layer < z_begin || layer >= z_end) atomicOr(bad, 1);
     top = layer == z_end - 1;
   }
   const unsigned b = __ballot_sync(0xffffffffu, top);

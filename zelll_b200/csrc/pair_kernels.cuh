@@ -932,11 +932,14 @@ __global__ void tile_list_kernel(const uint32_t* __restrict__ csr, uint32_t home
 
 // (energy, pair count, error flag = 0) -> three doubles for one all-reduce (the count is exact in f64
 // below 2^53; a rank whose step failed contributes (0, 0, 1) from the host instead)
+// flags / slab_flag: the build's own verdict (particle outside the window; halo overflow; box changed under a
+// speculative step) is folded in on the device, so no host round trip is needed before the collective.
 __global__ void pack_energy_count_kernel(const double* __restrict__ e, const unsigned long long* __restrict__ c,
+                                         const int* __restrict__ flags, const uint32_t* __restrict__ slab_flag,
                                          double* __restrict__ out3) {
   out3[0] = *e;
   out3[1] = (double)*c;
-  out3[2] = 0.0;
+  out3[2] = ((*flags & 1) || (*slab_flag & 7u)) ? 1.0 : 0.0;
 }
 
 // exclusive scan of the per-tile pair counts (a few 10^4 entries): one block, serial over chunks

@@ -60,7 +60,9 @@ struct Misc {
   double energy;           // finalize_kernel
   unsigned long long pair_total;
   uint32_t slab_count;     // slab_top_kernel: rows in the halo block
-  uint32_t slab_flag;      // slab_top_kernel: bit0 = a particle outside the slab
+  uint32_t slab_flag;      // bit0 = a particle outside the slab, bit1 = halo overflow, bit2 = box changed (speculative step)
+  uint32_t halo_n;         // slab-local step: halo rows received (counted on the device)
+  uint32_t pad2;
 };
 
 }  // namespace
@@ -147,6 +149,7 @@ struct zb_grid {
     // Measured neutral on B200 (LJ 1.159 unsplit vs 1.178 ms split at n = 10^7): the 5 k-instruction kernel
     // is not instruction-cache bound, so one launch stays the default.
     bool split = false;
+    bool slab_spec = true;  // ZB_SLAB_SPEC=0: native slab steps always wait for the box all-reduce
     uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
     uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
     // ZB_SPARSE: 0 = never use the compact-cell build (boxes beyond 2^31 cells are refused, as in round 1),
@@ -169,6 +172,18 @@ struct zb_grid {
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
   } nccl;
+  // slab-local step without host round trips: the halo count stays on the device and the build's verdict
+  // travels with the energy all-reduce; `slab_pending` = that verdict has not been looked at yet.  A step may
+  // also run SPECULATIVELY with the previous step's global box (no wait for the box all-reduce); the box is
+  // then checked on the device and, if it changed, every rank repeats the step (all see the same box).
+  struct SlabStep {
+    bool pending = false, spec = false, have_box = false;
+    double box[6] = {0, 0, 0, 0, 0, 0};  // (-inf, sup) of the last completed step, as all-reduced
+    int backoff = 0, penalty = 0;        // steps to run without speculation after a miss
+    void* buf = nullptr;
+    uint64_t n_local = 0, cap_rows = 0, halo_cap = 0;
+    uint32_t label_offset = 0;
+  } slab;
   DevBuf halo_send, halo_recv, halo_labels, red;  // halo blocks, halo labels, 8-double reduction scratch
   double* h_red = nullptr;                        // pinned mirror of `red`
   uint64_t n_local = 0, n_halo = 0;
@@ -197,6 +212,8 @@ struct zb_grid {
   double stage_ms[ZB_NSTAGES] = {0};
   uint64_t stage_launches[ZB_NSTAGES] = {0};
 };
+
+static int slab_collect(zb_grid* g, bool* redone);
 
 namespace {
 
@@ -393,7 +410,9 @@ template <class T>
 struct SlabHook {
   TopLayerOut<T> top;
   uint64_t n_cap;                              // upper bound of local + halo rows (buffer sizing)
-  std::function<int(uint64_t* n_halo)> exchange;
+  // trades halos; *halo_rows = how many rows the launch over the halo must cover (a capacity: the number
+  // actually received stays on the device, in misc->halo_n)
+  std::function<int(uint64_t* halo_rows)> exchange;
 };
 
 template <class T>
@@ -434,26 +453,26 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t& n, 
 
   const GridParams<T> p = make_params<T>(g);
   uint32_t* cursor = cursor_ptr(g);
-  auto count = [&](const T* rows, uint64_t m, const TopLayerOut<T>* top) {
+  auto count = [&](const T* rows, uint64_t m, const TopLayerOut<T>* top, const uint32_t* m_dev) {
     if (m == 0) return;
     StageSpan span(g, rows == xyz ? ZB_STAGE_COUNT : ZB_STAGE_OTHER);  // the halo rows' launch is not "the" K2
     const uint32_t blocks = (uint32_t)((m + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
     const TopLayerOut<T> tl = top ? *top : TopLayerOut<T>{};
     if (g->ndim == 3) {
-      if (top) count_kernel<T, 3, true><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
-      else count_kernel<T, 3, false><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
+      if (top) count_kernel<T, 3, true><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl, m_dev);
+      else count_kernel<T, 3, false><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl, m_dev);
     } else {
-      if (top) count_kernel<T, 2, true><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
-      else count_kernel<T, 2, false><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl);
+      if (top) count_kernel<T, 2, true><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl, m_dev);
+      else count_kernel<T, 2, false><<<blocks, kPointThreads, 0, g->stream>>>(rows, (uint32_t)m, p, cursor, &g->misc->flags, tl, m_dev);
     }
     g->launches++;
   };
-  count(xyz, n, hook ? &hook->top : nullptr);
+  count(xyz, n, hook ? &hook->top : nullptr, nullptr);
+  const uint64_t n_own = n;
+  uint64_t halo_rows = 0;
   if (hook) {
-    uint64_t n_halo = 0;
-    ZB_TRY(hook->exchange(&n_halo));
-    count(xyz + n * (uint64_t)g->ndim, n_halo, nullptr);
-    n += n_halo;
+    ZB_TRY(hook->exchange(&halo_rows));
+    count(xyz + n * (uint64_t)g->ndim, halo_rows, nullptr, &g->misc->halo_n);
   }
   {
     StageSpan span(g, ZB_STAGE_SCAN);
@@ -462,14 +481,16 @@ int build_sorted(zb_grid* g, const T* xyz, const LabelSrc& labels, uint64_t& n, 
                                                        &g->misc->tile_counter, &g->misc->nonempty);
   }
   g->launches++;
-  if (n > 0) {
+  if (n + halo_rows > 0) {
     StageSpan span(g, ZB_STAGE_SCATTER);
-    const uint32_t blocks = (uint32_t)((n + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
+    const uint64_t m = n + halo_rows;  // launch capacity; the kernel stops at n_own + *halo_n
+    const uint32_t blocks = (uint32_t)((m + kPointThreads * kPointIlp - 1) / (kPointThreads * kPointIlp));
     Rec<T>* sorted = static_cast<Rec<T>*>(g->sorted.p);
+    const uint32_t* n_dev = hook ? &g->misc->halo_n : nullptr;
     if (g->ndim == 3)
-      scatter_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
+      scatter_kernel<T, 3><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)m, p, cursor, sorted, (uint32_t)n_own, n_dev);
     else
-      scatter_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)n, p, cursor, sorted);
+      scatter_kernel<T, 2><<<blocks, kPointThreads, 0, g->stream>>>(xyz, labels, (uint32_t)m, p, cursor, sorted, (uint32_t)n_own, n_dev);
     g->launches++;
   }
   if (g->stable && n > 1) {
@@ -745,6 +766,21 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   if (g->pre_in_use >= 0) {  // the staging slot this build read is free again
     ZB_CUDA(cudaEventRecord(g->pre[g->pre_in_use].released, g->stream));
     g->pre_in_use = -1;
+  }
+  if (hook) {
+    // Native slab step: no host round trip here.  The build's verdict (window flag, slab flag, halo count)
+    // is copied to pinned memory behind the kernels and looked at by the first call that synchronises
+    // anyway (slab_validate; zb_grid_lj_energy_allreduce folds it into its all-reduce on the device).
+    ZB_CUDA(cudaMemcpyAsync(&g->h_misc->slab_count, &g->misc->slab_count, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            g->stream));
+    if (!g->info_event) ZB_CUDA(cudaEventCreateWithFlags(&g->info_event, cudaEventDisableTiming));
+    ZB_CUDA(cudaEventRecord(g->info_event, g->stream));
+    g->info_pending = true;
+    g->slab_check_pending = false;
+    g->slab.pending = true;
+    g->keys_changed = -1;
+    g->built = true;
+    return ZB_OK;
   }
   if (!sharded && !g->track_keys) {
     // Nothing here can fail any more: every particle lies inside its own bounding box (a NaN
@@ -1075,6 +1111,7 @@ int collect_info(zb_grid* g) {
 
 int check_built(zb_grid* g) {
   if (!g) return ZB_ERR_BAD_ARG;
+  if (g->slab.pending) ZB_TRY(slab_collect(g, nullptr));  // a native slab step reports its verdict lazily
   if (!g->built) return fail(g, ZB_ERR_NOT_BUILT, "grid has not been (successfully) built");
   return ZB_OK;
 }
@@ -1122,6 +1159,7 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   if (const char* e = getenv("ZB_PREFILTER")) g->tune.prefilter = (uint32_t)atoi(e);
   if (const char* e = getenv("ZB_SPLIT")) g->tune.split = atoi(e) != 0;
   if (const char* e = getenv("ZB_SPARSE")) g->tune.sparse = atoi(e);
+  if (const char* e = getenv("ZB_SLAB_SPEC")) g->tune.slab_spec = atoi(e) != 0;
   if (const char* e = getenv("ZB_STAGE_RECS")) {
     const long v = atol(e);
     if (v >= 64 && v <= 6144) g->tune.stage_recs = (uint32_t)v;
@@ -1392,6 +1430,10 @@ int zb_slab_top_layer(zb_grid* g, const void* xyz, uint64_t n, double inf_axis, 
 
 int zb_grid_info(zb_grid* g, zb_info* out) {
   if (!g || !out) return ZB_ERR_BAD_ARG;
+  if (g->slab.pending) {
+    ZB_TRY(enter(g));
+    ZB_TRY(slab_collect(g, nullptr));
+  }
   if (g->info_pending) {
     ZB_TRY(enter(g));
     ZB_TRY(collect_info(g));
@@ -1792,22 +1834,32 @@ int zb_comm_init(zb_grid* g, const char* nccl_lib_path, const void* unique_id128
 
 template <class T>
 static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows, const double* cutoff,
-                          uint32_t label_offset, uint64_t halo_cap, zb_slab_info* out) {
+                          uint32_t label_offset, uint64_t halo_cap, zb_slab_info* out, bool allow_spec) {
   auto& N = g->nccl;
   if (!N.comm) return fail(g, ZB_ERR_NOT_BUILT, "zb_comm_init has not been called");
   if (n_local > 2147483647ull || cap_rows < n_local) return fail(g, ZB_ERR_BAD_ARG, "bad n_local / cap_rows");
   if (!buf || !is_device_ptr(buf)) return fail(g, ZB_ERR_BAD_ARG, "buf must be device memory");
+  bool cutoff_changed = false;
   if (cutoff) {
     const T c = (T)*cutoff;
     if (!(c > (T)0) || !std::isfinite((double)c)) return fail(g, ZB_ERR_BAD_ARG, "cutoff must be positive and finite");
+    cutoff_changed = g->cutoff != (double)c;
     g->cutoff = (double)c;
   }
   g->built = false;
+  g->slab.pending = false;
   T* xyz = static_cast<T*>(buf);
   double* red = static_cast<double*>(g->red.p);
   const int nd = g->ndim;
+  // Speculate that the global box is the one of the last completed step (trajectory frames of a closed
+  // system, repeated analysis of one frame): no wait for the box all-reduce.  The box is still all-reduced
+  // and compared ON THE DEVICE; a mismatch surfaces with the energy all-reduce and the step is repeated.
+  const bool spec = allow_spec && g->tune.slab_spec && g->slab.have_box && g->slab.backoff == 0 && !cutoff_changed;
+  if (!spec && g->slab.backoff > 0) g->slab.backoff--;
 
-  // 1. global box: local K1 -> (-inf, sup) -> all-reduce(max) -> host
+  // slab_count / slab_flag / halo_n live apart from the rebuild's counters
+  ZB_CUDA(cudaMemsetAsync(&g->misc->slab_count, 0, 3 * sizeof(uint32_t), g->stream));
+  // 1. global box: local K1 -> (-inf, sup) -> all-reduce(max)
   if (n_local) {
     ZB_TRY(launch_bbox<T>(g, xyz, n_local));
     widen6_kernel<T><<<1, 32, 0, g->stream>>>(reinterpret_cast<const T*>(g->misc->out6), red, nd, 1);
@@ -1817,13 +1869,23 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
     ZB_CUDA(cudaMemcpyAsync(red, empty, sizeof empty, cudaMemcpyHostToDevice, g->stream));
   }
   ZB_NCCL(N.AllReduce(red, red, 6, ncclDouble, ncclMax, N.comm, g->stream));
-  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 6 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  if (spec) {
+    Box6 expect;
+    for (int k = 0; k < 6; ++k) expect.v[k] = g->slab.box[k];
+    spec_check_kernel<<<1, 32, 0, g->stream>>>(red, expect, &g->misc->slab_flag);
+    g->launches++;
+  } else {
+    ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 6 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    for (int k = 0; k < 6; ++k) g->slab.box[k] = g->h_red[k];
+    g->slab.have_box = true;
+  }
+  g->slab.spec = spec;
   double inf[3] = {0, 0, 0}, sup[3] = {0, 0, 0};
   bool any = true;
   for (int d = 0; d < nd; ++d) {
-    inf[d] = -g->h_red[d];
-    sup[d] = g->h_red[3 + d];
+    inf[d] = -g->slab.box[d];
+    sup[d] = g->slab.box[3 + d];
     any = any && std::isfinite(inf[d]) && std::isfinite(sup[d]);
   }
   if (!any)  // no particle anywhere: Aabb of an empty set is zeros (util.rs:41)
@@ -1845,29 +1907,27 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
 
   // 2 + 3. sharded rebuild with the imposed box.  K2 over the local rows also extracts this slab's top
   //    layer (no extra pass over the input); the hook then trades halos -- top layer -> rank + 1, top
-  //    layer of rank - 1 -> behind the local rows -- and K2 counts the few received rows; K3, K4 run
-  //    over local + halo rows.  Labels come from (offset + i | halo labels).
+  //    layer of rank - 1 -> behind the local rows -- and K2 counts the received rows; K3, K4 run over
+  //    local + halo rows.  The number of halo rows never visits the host: the launches are sized for the
+  //    capacity and stop at the count the unpack kernel left in misc->halo_n.
+  const uint64_t room = std::min<uint64_t>(halo_cap, cap_rows - n_local);  // halo rows buf can take
   const size_t block = (halo_cap + 1) * 4 * sizeof(T);
   ZB_TRY(reserve(g, g->halo_send, block));
   ZB_TRY(reserve(g, g->halo_recv, block));
   ZB_TRY(reserve(g, g->halo_labels, std::max<uint64_t>(halo_cap, 1) * 4));
-  // slab_count / slab_flag live apart from the rebuild's counters
-  ZB_CUDA(cudaMemsetAsync(&g->misc->slab_count, 0, 2 * sizeof(uint32_t), g->stream));
-  uint64_t n_halo = 0;
   SlabHook<T> hook;
   hook.top.out = static_cast<T*>(g->halo_send.p);
   hook.top.cap = (uint32_t)std::min<uint64_t>(halo_cap, 0xfffffff0ull);
   hook.top.count = &g->misc->slab_count;
   hook.top.bad = reinterpret_cast<int*>(&g->misc->slab_flag);
   hook.top.label_offset = label_offset;
-  hook.n_cap = std::min<uint64_t>(cap_rows, n_local + halo_cap);
-  hook.exchange = [&](uint64_t* got) -> int {
-    *got = 0;
+  hook.n_cap = n_local + room;
+  hook.exchange = [&](uint64_t* halo_rows) -> int {
+    *halo_rows = 0;
     // the block header (row 0) carries the row count to the receiver
     halo_header_kernel<T><<<1, 1, 0, g->stream>>>(&g->misc->slab_count, hook.top.cap, static_cast<T*>(g->halo_send.p));
     g->launches++;
     ZB_CUDA(cudaGetLastError());
-    g->slab_check_pending = true;
     const bool up = N.rank + 1 < N.world, down = N.rank > 0;
     if (up || down) {
       ZB_NCCL(N.GroupStart());
@@ -1875,30 +1935,37 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
       if (down) ZB_NCCL(N.Recv(g->halo_recv.p, block, ncclChar, N.rank - 1, N.comm, g->stream));
       ZB_NCCL(N.GroupEnd());
     }
-    if (!down) return ZB_OK;
-    ZB_CUDA(cudaMemcpyAsync(g->h_red, g->halo_recv.p, sizeof(T), cudaMemcpyDeviceToHost, g->stream));
-    ZB_CUDA(cudaStreamSynchronize(g->stream));
-    n_halo = (uint64_t) * reinterpret_cast<const T*>(g->h_red);
-    if (n_halo > halo_cap) return fail(g, ZB_ERR_CAPACITY, "the neighbour's top layer exceeds halo_cap = %llu rows", (unsigned long long)halo_cap);
-    if (n_local + n_halo > cap_rows) return fail(g, ZB_ERR_CAPACITY, "buf has no room for %llu halo rows", (unsigned long long)n_halo);
-    if (n_halo) {
-      const uint32_t blocks = (uint32_t)((n_halo + 255) / 256);
-      if (nd == 3)
-        halo_unpack_kernel<T, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)halo_cap,
-                                                                xyz + n_local * 3, static_cast<uint32_t*>(g->halo_labels.p));
-      else
-        halo_unpack_kernel<T, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)halo_cap,
-                                                                xyz + n_local * 2, static_cast<uint32_t*>(g->halo_labels.p));
-      g->launches++;
-      ZB_CUDA(cudaGetLastError());
+    if (!down || room == 0) {
+      if (down) {  // no room at all behind the local rows: any halo row is an overflow
+        halo_unpack_kernel<T, 3><<<1, 32, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), 0u, xyz, nullptr,
+                                                           &g->misc->halo_n, &g->misc->slab_flag);
+        g->launches++;
+      }
+      return ZB_OK;  // misc->halo_n stays 0
     }
-    *got = n_halo;
+    const uint32_t blocks = (uint32_t)((room + 255) / 256);
+    if (nd == 3)
+      halo_unpack_kernel<T, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)room, xyz + n_local * 3,
+                                                              static_cast<uint32_t*>(g->halo_labels.p), &g->misc->halo_n,
+                                                              &g->misc->slab_flag);
+    else
+      halo_unpack_kernel<T, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)room, xyz + n_local * 2,
+                                                              static_cast<uint32_t*>(g->halo_labels.p), &g->misc->halo_n,
+                                                              &g->misc->slab_flag);
+    g->launches++;
+    ZB_CUDA(cudaGetLastError());
+    *halo_rows = room;
     return ZB_OK;
   };
   LabelSrc ls{nullptr, static_cast<const uint32_t*>(g->halo_labels.p), label_offset, (uint32_t)n_local};
   ZB_TRY(rebuild_impl<T>(g, xyz, n_local, nullptr, nullptr, inf, sup, z_begin, z_end, true, &ls, &hook));
   g->n_local = n_local;
-  g->n_halo = n_halo;
+  g->n_halo = 0;  // known once the step's verdict has been collected (slab_validate)
+  g->slab.buf = buf;
+  g->slab.n_local = n_local;
+  g->slab.cap_rows = cap_rows;
+  g->slab.halo_cap = halo_cap;
+  g->slab.label_offset = label_offset;
   if (out) {
     memset(out, 0, sizeof *out);
     for (int d = 0; d < 3; ++d) {
@@ -1909,7 +1976,55 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
     out->z_begin = z_begin;
     out->z_end = z_end;
     out->n_local = n_local;
-    out->n_halo = n_halo;
+    out->n_halo = ~0ull;  // counted on the device: zb_grid_info().n - n_local after the next synchronising call
+  }
+  return ZB_OK;
+}
+
+static int slab_step(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows, const double* cutoff, uint32_t label_offset,
+                     uint64_t halo_cap, zb_slab_info* out, bool allow_spec) {
+  return g->dtype == ZB_F32 ? slab_step_impl<float>(g, buf, n_local, cap_rows, cutoff, label_offset, halo_cap, out, allow_spec)
+                            : slab_step_impl<double>(g, buf, n_local, cap_rows, cutoff, label_offset, halo_cap, out, allow_spec);
+}
+
+// The verdict of a slab step whose copies have reached the host (the caller has synchronised the stream or
+// waits here).  A speculative step whose box changed is repeated without speculation -- by EVERY rank: all
+// compare the same all-reduced box with the same remembered one.  *redone tells the caller to repeat what it
+// had queued behind the step.
+static int slab_collect(zb_grid* g, bool* redone) {
+  if (redone) *redone = false;
+  if (!g->slab.pending) return ZB_OK;
+  ZB_CUDA(cudaEventSynchronize(g->info_event));
+  g->slab.pending = false;
+  const uint32_t flag = g->h_misc->slab_flag;
+  if (g->slab.spec && (flag & 4u)) {
+    g->slab.penalty = std::min(64, std::max(2, 2 * g->slab.penalty));
+    g->slab.backoff = g->slab.penalty;
+    ZB_TRY(slab_step(g, g->slab.buf, g->slab.n_local, g->slab.cap_rows, nullptr, g->slab.label_offset, g->slab.halo_cap, nullptr,
+                     false));
+    ZB_CUDA(cudaEventSynchronize(g->info_event));
+    g->slab.pending = false;
+    if (redone) *redone = true;
+  } else if (g->slab.spec) {
+    g->slab.penalty = 0;
+  }
+  g->info_pending = false;
+  g->n_cells_nonempty = g->h_misc->nonempty;
+  const uint32_t f2 = g->h_misc->slab_flag;
+  g->n_halo = g->h_misc->halo_n;
+  g->n = g->n_local + g->n_halo;
+  if (f2 & 2u) {
+    g->built = false;
+    return fail(g, ZB_ERR_CAPACITY, "the neighbour's top layer exceeds halo_cap = %llu rows (or the spare rows of buf)",
+                (unsigned long long)g->slab.halo_cap);
+  }
+  if (f2 & 1u) {
+    g->built = false;
+    return fail(g, ZB_ERR_OUT_OF_WINDOW, "slab-local input held a particle outside its own layers");
+  }
+  if (g->h_misc->flags & 1) {
+    g->built = false;
+    return fail(g, ZB_ERR_OUT_OF_WINDOW, "a particle lies outside the imposed box / slab window");
   }
   return ZB_OK;
 }
@@ -1919,8 +2034,7 @@ extern "C" {
 int zb_grid_rebuild_slab_local(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows, const double* cutoff_or_null,
                                uint32_t label_offset, uint64_t halo_cap, zb_slab_info* out) {
   ZB_TRY(enter(g));
-  return g->dtype == ZB_F32 ? slab_step_impl<float>(g, buf, n_local, cap_rows, cutoff_or_null, label_offset, halo_cap, out)
-                            : slab_step_impl<double>(g, buf, n_local, cap_rows, cutoff_or_null, label_offset, halo_cap, out);
+  return slab_step(g, buf, n_local, cap_rows, cutoff_or_null, label_offset, halo_cap, out, true);
 }
 
 int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs) {
@@ -1931,27 +2045,37 @@ int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, doubl
   if (cmp < 1 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "lj energy needs a distance filter (cmp LT or LE)");
   // A rank whose slab step failed (halo overflow, particle outside its layers, ...) still enters the
   // collective -- with a raised error flag in the third slot -- so that its peers are not left hanging;
-  // every rank then reports the failure.
+  // every rank then reports the failure.  The flag is raised on the DEVICE from the build's own flags, so
+  // the whole step needs ONE host round trip: this read.
   double* red = static_cast<double*>(g->red.p);
-  int local_rc = g->built ? ZB_OK : ZB_ERR_NOT_BUILT;
-  if (local_rc == ZB_OK) local_rc = g->dtype == ZB_F32 ? lj_impl<float>(g, cmp, filter_cutoff) : lj_impl<double>(g, cmp, filter_cutoff);
-  if (local_rc == ZB_OK) {
-    // (energy, pair count as f64: exact below 2^53, error flag) -> one all-reduce(sum) -> host
-    pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, red);
-    g->launches++;
-  } else {
-    const double bad[3] = {0.0, 0.0, 1.0};
-    ZB_CUDA(cudaMemcpyAsync(red, bad, sizeof bad, cudaMemcpyHostToDevice, g->stream));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int local_rc = g->built ? ZB_OK : ZB_ERR_NOT_BUILT;
+    if (local_rc == ZB_OK)
+      local_rc = g->dtype == ZB_F32 ? lj_impl<float>(g, cmp, filter_cutoff) : lj_impl<double>(g, cmp, filter_cutoff);
+    if (local_rc == ZB_OK) {
+      // (energy, pair count as f64: exact below 2^53, error flag) -> one all-reduce(sum) -> host
+      pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, &g->misc->flags,
+                                                       &g->misc->slab_flag, red);
+      g->launches++;
+    } else {
+      const double bad[3] = {0.0, 0.0, 1.0};
+      ZB_CUDA(cudaMemcpyAsync(red, bad, sizeof bad, cudaMemcpyHostToDevice, g->stream));
+    }
+    ZB_NCCL(N.AllReduce(red, red, 3, ncclDouble, ncclSum, N.comm, g->stream));
+    ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 3 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    ZB_CUDA(cudaStreamSynchronize(g->stream));
+    if (local_rc != ZB_OK) return local_rc;  // g->err holds this rank's own reason
+    bool redone = false;
+    const int rc = slab_collect(g, &redone);  // no wait: the stream has just been synchronised
+    if (redone && rc == ZB_OK) continue;      // the box had changed under a speculative step: every rank repeats
+    if (rc != ZB_OK) return rc;
+    if (g->h_red[2] != 0.0)
+      return fail(g, ZB_ERR_NOT_BUILT, "%d rank(s) failed their slab step; the all-reduced energy is not valid", (int)g->h_red[2]);
+    *energy = g->h_red[0];
+    if (n_pairs) *n_pairs = (uint64_t)g->h_red[1];
+    return ZB_OK;
   }
-  ZB_NCCL(N.AllReduce(red, red, 3, ncclDouble, ncclSum, N.comm, g->stream));
-  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 3 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-  ZB_CUDA(cudaStreamSynchronize(g->stream));
-  if (local_rc != ZB_OK) return local_rc;  // g->err holds this rank's own reason
-  if (g->h_red[2] != 0.0)
-    return fail(g, ZB_ERR_NOT_BUILT, "%d rank(s) failed their slab step; the all-reduced energy is not valid", (int)g->h_red[2]);
-  *energy = g->h_red[0];
-  if (n_pairs) *n_pairs = (uint64_t)g->h_red[1];
-  return ZB_OK;
+  return fail(g, ZB_ERR_NOT_BUILT, "slab step could not be completed");
 }
 
 int zb_grid_profile(zb_grid* g, int enable) {

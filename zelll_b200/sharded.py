@@ -183,6 +183,11 @@ class NativeSlabGrid(ShardedCellGrid):
         self.slab = info
         return info
 
+    @property
+    def n_halo(self) -> int:
+        """Halo rows of the last step (counted on the device; asking synchronises the step)."""
+        return int(self.info().n) - int(self.slab.n_local) if self.slab is not None else 0
+
     def lj_energy_allreduce(self, cutoff: Optional[float] = None, cmp="lt", return_pairs: bool = False):
         code, fc = self._filter(cutoff, cmp)
         e, m = C.c_double(0.0), C.c_uint64(0)
