@@ -49,7 +49,9 @@ enum zb_status {
   ZB_ERR_CUDA = 2,          /* CUDA runtime error; see zb_last_error */
   ZB_ERR_CAPACITY = 3,      /* caller's output buffer too small; *n_out holds the needed size */
   ZB_ERR_TOO_MANY = 4,      /* n > i32::MAX (src/cellgrid/flatindex.rs:87) */
-  ZB_ERR_GRID_TOO_LARGE = 5,/* bounding box / cutoff needs more cells than the engine can index */
+  ZB_ERR_GRID_TOO_LARGE = 5,/* bounding box / cutoff needs more cells than the engine can index (2^62; boxes
+                               beyond 2^31 cells, or with far more cells than particles, are built as compact
+                               sorted non-empty cells in O(n) memory; slab-sharded grids: 2^31) */
   ZB_ERR_NOT_BUILT = 6,
   ZB_ERR_OUT_OF_WINDOW = 7  /* sharded rebuild: a particle lies outside the imposed box/slab */
 };
@@ -105,7 +107,9 @@ int zb_grid_rebuild(zb_grid* g, const void* xyz, uint64_t n, const double* cutof
  * the copy overlaps the build / pair / LJ kernels of the current frame (two staging slots: call it
  * for frame k+1 before zb_grid_rebuild of frame k).  A zb_grid_rebuild with the same (xyz, n) uses
  * the staged copy instead of copying again.  xyz should be pinned memory
- * (pageable memory makes the copy synchronous); the caller must not modify it until that rebuild. */
+ * (pageable memory makes the copy synchronous); the caller must neither modify nor free it until that
+ * rebuild (slots are matched by address; only zb_grid_rebuild consumes them, and a slot two rebuilds in a
+ * row did not ask for is dropped). */
 int zb_grid_prefetch(zb_grid* g, const void* xyz_host, uint64_t n);
 /* Orders the handle's stream behind every copy zb_grid_prefetch has started (no host stall). */
 int zb_grid_prefetch_wait(zb_grid* g);
@@ -156,7 +160,10 @@ typedef struct zb_slab_info {
   int32_t shape[3];
   int32_t reserved;
   int64_t z_begin, z_end; /* layers of the slab axis this rank owns */
-  uint64_t n_local, n_halo;
+  uint64_t n_local;
+  uint64_t n_halo;        /* UINT64_MAX from zb_grid_rebuild_slab_local: the halo rows are counted on the
+                             device; zb_grid_info().n - n_local gives the number once the step's verdict
+                             has been collected (any later call that synchronises) */
 } zb_slab_info;
 
 /* rank 0 creates the 128-byte NCCL unique id; the launcher distributes it to all ranks */
@@ -165,12 +172,22 @@ int zb_comm_init(zb_grid* g, const char* nccl_lib_path, const void* unique_id128
 
 /* Slab-local rebuild: buf (DEVICE, cap_rows x ndim values of the grid's dtype) holds this rank's
  * n_local particles -- exactly those of its own layers -- in its first rows; the halo rows received
- * from rank - 1 are appended behind them.  Labels are label_offset + row for local particles. */
+ * from rank - 1 are appended behind them.  Labels are label_offset + row for local particles.
+ * The grid needs at least one layer per rank along the slab axis (ZB_ERR_BAD_ARG otherwise, on every rank).
+ * The call returns WITHOUT a host round trip for the halo count or the build's verdict (a particle outside
+ * its slab, a halo larger than halo_cap / the spare rows of buf): those are reported by the next call on the
+ * handle that synchronises -- zb_grid_lj_energy_allreduce folds them into its all-reduce, so every rank
+ * learns of any rank's failure.  A step whose all-reduced bounding box equals the previous step's also skips
+ * the wait for the box (it is checked on the device; if it did change, the step is repeated transparently,
+ * by every rank).  buf must stay unchanged until that next synchronising call. */
 int zb_grid_rebuild_slab_local(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_rows,
                                const double* cutoff_or_null, uint32_t label_offset, uint64_t halo_cap,
                                zb_slab_info* out);
 
-/* zb_grid_lj_energy followed by the all-reduce(sum) of energy and pair count over the communicator */
+/* zb_grid_lj_energy followed by the all-reduce(sum) of energy and pair count over the communicator: the one
+ * host round trip of a slab step.  Every rank must call it, also a rank whose zb_grid_rebuild_slab_local
+ * failed (it then contributes an error flag instead of hanging its peers); all ranks return an error if
+ * any rank's step failed. */
 int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, double* energy, uint64_t* n_pairs);
 
 /* -- inspection ---------------------------------------------------------------------------- */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzelll_b200.so")
 SOURCES = ["zelll_b200.cu"]
-HEADERS = ["common.cuh", "build_kernels.cuh", "pair_kernels.cuh", "pair_pf_kernels.cuh", "query_kernels.cuh", "sparse_kernels.cuh"]
+HEADERS = ["common.cuh", "build_kernels.cuh", "pair_kernels.cuh", "pair_pf_kernels.cuh", "p2p_kernels.cuh", "query_kernels.cuh", "sparse_kernels.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -939,7 +939,7 @@ __global__ void pack_energy_count_kernel(const double* __restrict__ e, const uns
                                          double* __restrict__ out3) {
   out3[0] = *e;
   out3[1] = (double)*c;
-  out3[2] = ((*flags & 1) || (*slab_flag & 7u)) ? 1.0 : 0.0;
+  out3[2] = ((*flags & 1) || (*slab_flag & 15u)) ? 1.0 : 0.0;
 }
 
 // exclusive scan of the per-tile pair counts (a few 10^4 entries): one block, serial over chunks

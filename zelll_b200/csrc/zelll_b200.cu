@@ -27,6 +27,7 @@
 #include "build_kernels.cuh"
 #include "pair_kernels.cuh"
 #include "pair_pf_kernels.cuh"
+#include "p2p_kernels.cuh"
 #include "query_kernels.cuh"
 #include "sparse_kernels.cuh"
 
@@ -62,7 +63,7 @@ struct Misc {
   uint32_t slab_count;     // slab_top_kernel: rows in the halo block
   uint32_t slab_flag;      // bit0 = a particle outside the slab, bit1 = halo overflow, bit2 = box changed (speculative step)
   uint32_t halo_n;         // slab-local step: halo rows received (counted on the device)
-  uint32_t pad2;
+  unsigned halo_ticket;    // p2p_halo_push_kernel: blocks finished (self re-arming)
 };
 
 }  // namespace
@@ -150,6 +151,8 @@ struct zb_grid {
     // is not instruction-cache bound, so one launch stays the default.
     bool split = false;
     bool slab_spec = true;  // ZB_SLAB_SPEC=0: native slab steps always wait for the box all-reduce
+    bool p2p = true;        // ZB_P2P=0: the slab step's exchanges go through NCCL instead of mapped peer memory
+    uint32_t p2p_halo_rows = 8192;  // ZB_P2P_HALO_ROWS: rows of the mapped halo blocks
     uint32_t stage_recs = 0;   // ZB_STAGE_RECS: records per shared-memory stage (0 = default)
     uint32_t tile_cells = 0;   // ZB_TILE_CELLS: home cells per tile (0 = derived from the load)
     // ZB_SPARSE: 0 = never use the compact-cell build (boxes beyond 2^31 cells are refused, as in round 1),
@@ -168,6 +171,7 @@ struct zb_grid {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -184,6 +188,17 @@ struct zb_grid {
     uint64_t n_local = 0, cap_rows = 0, halo_cap = 0;
     uint32_t label_offset = 0;
   } slab;
+  // exchanges over NVLink peer memory instead of NCCL (p2p_kernels.cuh): every rank's mailbox is mapped into
+  // every process of the node at zb_comm_init
+  struct P2p {
+    bool ok = false;
+    void* local = nullptr;
+    void* opened[kP2pMaxWorld] = {nullptr};
+    P2pPeers peers{};
+    uint64_t halo_rows = 0;    // capacity of the mapped halo blocks (rows)
+    size_t block_bytes = 0;
+    unsigned long long seq_box = 0, seq_energy = 0, seq_halo = 0;
+  } p2p;
   DevBuf halo_send, halo_recv, halo_labels, red;  // halo blocks, halo labels, 8-double reduction scratch
   double* h_red = nullptr;                        // pinned mirror of `red`
   uint64_t n_local = 0, n_halo = 0;
@@ -1063,7 +1078,7 @@ int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* pla
 }
 
 template <class T>
-int lj_impl(zb_grid* g, int cmp, double fc) {
+int lj_impl(zb_grid* g, int cmp, double fc, uint32_t* blocks_out = nullptr) {
   PairPlan pl = plan_pairs<T>(g, LjConsumer<T>::kWarpSmemBytes, LjConsumer<T>::kPfWarpSmemBytes, cmp, fc, 2u);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
   ZB_TRY(reserve(g, g->block_energy, (size_t)pl.blocks * 8));
@@ -1076,7 +1091,8 @@ int lj_impl(zb_grid* g, int cmp, double fc) {
     ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
     ZB_CUDA(cudaMemsetAsync(g->block_energy.p, 0, (size_t)pl.blocks * 8, g->stream));
   }
-  ZB_TRY(finalize(g, true, pl.blocks));
+  if (blocks_out) *blocks_out = pl.blocks;  // the caller folds the per-block partials itself (p2p_energy_kernel)
+  else ZB_TRY(finalize(g, true, pl.blocks));
   return ZB_OK;
 }
 
@@ -1160,6 +1176,11 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   if (const char* e = getenv("ZB_SPLIT")) g->tune.split = atoi(e) != 0;
   if (const char* e = getenv("ZB_SPARSE")) g->tune.sparse = atoi(e);
   if (const char* e = getenv("ZB_SLAB_SPEC")) g->tune.slab_spec = atoi(e) != 0;
+  if (const char* e = getenv("ZB_P2P")) g->tune.p2p = atoi(e) != 0;
+  if (const char* e = getenv("ZB_P2P_HALO_ROWS")) {
+    const long v = atol(e);
+    if (v >= 64 && v <= (1 << 24)) g->tune.p2p_halo_rows = (uint32_t)v;
+  }
   if (const char* e = getenv("ZB_STAGE_RECS")) {
     const long v = atol(e);
     if (v >= 64 && v <= 6144) g->tune.stage_recs = (uint32_t)v;
@@ -1205,6 +1226,9 @@ void zb_grid_destroy(zb_grid* g) {
   }
   if (g->info_event) cudaEventDestroy(g->info_event);
   if (g->bbox_event) cudaEventDestroy(g->bbox_event);
+  for (void* o : g->p2p.opened)
+    if (o) cudaIpcCloseMemHandle(o);
+  if (g->p2p.local) cudaFree(g->p2p.local);
   if (g->nccl.comm && g->nccl.CommDestroy) g->nccl.CommDestroy(g->nccl.comm);
   if (g->nccl.dl) dlclose(g->nccl.dl);
   if (g->h_red) cudaFreeHost(g->h_red);
@@ -1784,11 +1808,77 @@ static int nccl_load(zb_grid* g, const char* path) {
   N.AllReduce = reinterpret_cast<decltype(N.AllReduce)>(sym("ncclAllReduce"));
   N.Send = reinterpret_cast<decltype(N.Send)>(sym("ncclSend"));
   N.Recv = reinterpret_cast<decltype(N.Recv)>(sym("ncclRecv"));
+  N.AllGather = reinterpret_cast<decltype(N.AllGather)>(sym("ncclAllGather"));
   N.GroupStart = reinterpret_cast<decltype(N.GroupStart)>(sym("ncclGroupStart"));
   N.GroupEnd = reinterpret_cast<decltype(N.GroupEnd)>(sym("ncclGroupEnd"));
   N.GetErrorString = reinterpret_cast<decltype(N.GetErrorString)>(sym("ncclGetErrorString"));
   if (!N.CommInitRank || !N.AllReduce || !N.Send || !N.Recv || !N.GroupStart || !N.GroupEnd)
     return fail(g, ZB_ERR_CUDA, "NCCL library lacks a required symbol");
+  return ZB_OK;
+}
+
+// Map every rank's mailbox into this process (p2p_kernels.cuh).  Collective over the new communicator; any
+// failure on any rank (no peer access, IPC refused, more than kP2pMaxWorld ranks) leaves ALL ranks on NCCL.
+static int p2p_setup(zb_grid* g) {
+  auto& N = g->nccl;
+  auto& P = g->p2p;
+  P.ok = false;
+  if (N.world < 2) return ZB_OK;
+  int ok = (g->tune.p2p && N.world <= kP2pMaxWorld && N.AllGather) ? 1 : 0;
+  P.halo_rows = g->tune.p2p_halo_rows;
+  P.block_bytes = ((size_t)P.halo_rows + 1) * 4 * sizeof(double);
+  const size_t bytes = P2pLayout::total(P.block_bytes);
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok) {
+    if (cudaMalloc(&P.local, bytes) != cudaSuccess || cudaMemset(P.local, 0, bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, P.local) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  // all-gather the handles (and each rank's verdict so far) through the communicator
+  constexpr size_t kRec = sizeof(cudaIpcMemHandle_t) + 8;
+  std::vector<unsigned char> h_all(kRec * (size_t)N.world, 0), h_mine(kRec, 0);
+  memcpy(h_mine.data(), &mine, sizeof mine);
+  h_mine[sizeof mine] = (unsigned char)ok;
+  DevBuf d_mine, d_all;
+  ZB_TRY(reserve(g, d_mine, kRec));
+  ZB_TRY(reserve(g, d_all, kRec * (size_t)N.world));
+  ZB_CUDA(cudaMemcpyAsync(d_mine.p, h_mine.data(), kRec, cudaMemcpyHostToDevice, g->stream));
+  ZB_NCCL(N.AllGather(d_mine.p, d_all.p, kRec, ncclChar, N.comm, g->stream));
+  ZB_CUDA(cudaMemcpyAsync(h_all.data(), d_all.p, kRec * (size_t)N.world, cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  free_buf(d_mine);
+  free_buf(d_all);
+  for (int r = 0; r < N.world; ++r) ok = ok && h_all[kRec * r + sizeof mine];
+  if (ok) {
+    for (int r = 0; r < N.world && ok; ++r) {
+      if (r == N.rank) {
+        P.peers.base[r] = static_cast<unsigned char*>(P.local);
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &h_all[kRec * r], sizeof h);
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      P.opened[r] = ptr;
+      P.peers.base[r] = static_cast<unsigned char*>(ptr);
+    }
+  }
+  // second agreement: did every rank manage to open every handle?
+  double* red = static_cast<double*>(g->red.p);
+  const double v = ok ? 1.0 : 0.0;
+  ZB_CUDA(cudaMemcpyAsync(red, &v, sizeof v, cudaMemcpyHostToDevice, g->stream));
+  ZB_NCCL(N.AllReduce(red, red, 1, ncclDouble, ncclMin, N.comm, g->stream));
+  ZB_CUDA(cudaMemcpyAsync(g->h_red, red, sizeof v, cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  P.ok = g->h_red[0] == 1.0;
+  P.seq_box = P.seq_energy = P.seq_halo = 0;
   return ZB_OK;
 }
 
@@ -1825,9 +1915,9 @@ int zb_comm_init(zb_grid* g, const char* nccl_lib_path, const void* unique_id128
   ZB_NCCL(g->nccl.CommInitRank(&g->nccl.comm, world, id, rank));
   g->nccl.world = world;
   g->nccl.rank = rank;
-  ZB_TRY(reserve(g, g->red, 8 * sizeof(double)));
+  ZB_TRY(reserve(g, g->red, 64 * sizeof(double)));
   if (!g->h_red) ZB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g->h_red), 8 * sizeof(double)));
-  return ZB_OK;
+  return p2p_setup(g);
 }
 
 }  // extern "C"
@@ -1859,22 +1949,35 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
 
   // slab_count / slab_flag / halo_n live apart from the rebuild's counters
   ZB_CUDA(cudaMemsetAsync(&g->misc->slab_count, 0, 3 * sizeof(uint32_t), g->stream));
-  // 1. global box: local K1 -> (-inf, sup) -> all-reduce(max)
-  if (n_local) {
-    ZB_TRY(launch_bbox<T>(g, xyz, n_local));
-    widen6_kernel<T><<<1, 32, 0, g->stream>>>(reinterpret_cast<const T*>(g->misc->out6), red, nd, 1);
-    g->launches++;
-  } else {
-    const double empty[6] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    ZB_CUDA(cudaMemcpyAsync(red, empty, sizeof empty, cudaMemcpyHostToDevice, g->stream));
-  }
-  ZB_NCCL(N.AllReduce(red, red, 6, ncclDouble, ncclMax, N.comm, g->stream));
-  if (spec) {
-    Box6 expect;
+  // 1. global box: local K1 -> (-inf, sup) -> all-reduce(max) [-> compared with the assumed box]
+  if (g->p2p.ok) {
+    // over peer memory: widen + all-reduce + check in ONE launch behind K1
+    if (n_local) ZB_TRY(launch_bbox<T>(g, xyz, n_local));
+    Box6v expect;
     for (int k = 0; k < 6; ++k) expect.v[k] = g->slab.box[k];
-    spec_check_kernel<<<1, 32, 0, g->stream>>>(red, expect, &g->misc->slab_flag);
+    p2p_box_kernel<T><<<1, 32, 0, g->stream>>>(g->p2p.peers, N.world, N.rank, ++g->p2p.seq_box,
+                                               reinterpret_cast<const T*>(g->misc->out6), nd, n_local ? 1 : 0, red, spec ? 1 : 0, expect,
+                                               &g->misc->slab_flag);
     g->launches++;
+    ZB_CUDA(cudaGetLastError());
   } else {
+    if (n_local) {
+      ZB_TRY(launch_bbox<T>(g, xyz, n_local));
+      widen6_kernel<T><<<1, 32, 0, g->stream>>>(reinterpret_cast<const T*>(g->misc->out6), red, nd, 1);
+      g->launches++;
+    } else {
+      const double empty[6] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      ZB_CUDA(cudaMemcpyAsync(red, empty, sizeof empty, cudaMemcpyHostToDevice, g->stream));
+    }
+    ZB_NCCL(N.AllReduce(red, red, 6, ncclDouble, ncclMax, N.comm, g->stream));
+    if (spec) {
+      Box6 expect;
+      for (int k = 0; k < 6; ++k) expect.v[k] = g->slab.box[k];
+      spec_check_kernel<<<1, 32, 0, g->stream>>>(red, expect, &g->misc->slab_flag);
+      g->launches++;
+    }
+  }
+  if (!spec) {
     ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 6 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
     ZB_CUDA(cudaStreamSynchronize(g->stream));
     for (int k = 0; k < 6; ++k) g->slab.box[k] = g->h_red[k];
@@ -1924,12 +2027,34 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
   hook.n_cap = n_local + room;
   hook.exchange = [&](uint64_t* halo_rows) -> int {
     *halo_rows = 0;
-    // the block header (row 0) carries the row count to the receiver
-    halo_header_kernel<T><<<1, 1, 0, g->stream>>>(&g->misc->slab_count, hook.top.cap, static_cast<T*>(g->halo_send.p));
-    g->launches++;
-    ZB_CUDA(cudaGetLastError());
     const bool up = N.rank + 1 < N.world, down = N.rank > 0;
-    if (up || down) {
+    // over mapped peer memory when the halo block fits the mapped one (every rank passes the same halo_cap),
+    // else NCCL send / recv of the fixed-size block
+    const bool p2p = g->p2p.ok && halo_cap <= g->p2p.halo_rows;
+    const T* recv_block = static_cast<const T*>(g->halo_recv.p);
+    if (p2p) {
+      const unsigned long long seq = ++g->p2p.seq_halo;
+      const int parity = (int)(seq & 1ull);
+      if (up) {
+        unsigned char* peer = g->p2p.peers.base[N.rank + 1];
+        p2p_halo_push_kernel<T><<<8, 256, 0, g->stream>>>(
+            static_cast<const T*>(g->halo_send.p), &g->misc->slab_count, hook.top.cap,
+            reinterpret_cast<T*>(peer + P2pLayout::halo_block_off(parity, g->p2p.block_bytes)),
+            reinterpret_cast<unsigned long long*>(peer + P2pLayout::halo_flag_off(parity)), seq, &g->misc->halo_ticket);
+        g->launches++;
+      }
+      if (down) {
+        unsigned char* mine = g->p2p.peers.base[N.rank];
+        p2p_halo_wait_kernel<<<1, 32, 0, g->stream>>>(reinterpret_cast<const unsigned long long*>(mine + P2pLayout::halo_flag_off(parity)), seq,
+                                                      &g->misc->slab_flag);
+        g->launches++;
+        recv_block = reinterpret_cast<const T*>(mine + P2pLayout::halo_block_off(parity, g->p2p.block_bytes));
+      }
+      ZB_CUDA(cudaGetLastError());
+    } else if (up || down) {
+      // the block header (row 0) carries the row count to the receiver
+      halo_header_kernel<T><<<1, 1, 0, g->stream>>>(&g->misc->slab_count, hook.top.cap, static_cast<T*>(g->halo_send.p));
+      g->launches++;
       ZB_NCCL(N.GroupStart());
       if (up) ZB_NCCL(N.Send(g->halo_send.p, block, ncclChar, N.rank + 1, N.comm, g->stream));
       if (down) ZB_NCCL(N.Recv(g->halo_recv.p, block, ncclChar, N.rank - 1, N.comm, g->stream));
@@ -1937,19 +2062,18 @@ static int slab_step_impl(zb_grid* g, void* buf, uint64_t n_local, uint64_t cap_
     }
     if (!down || room == 0) {
       if (down) {  // no room at all behind the local rows: any halo row is an overflow
-        halo_unpack_kernel<T, 3><<<1, 32, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), 0u, xyz, nullptr,
-                                                           &g->misc->halo_n, &g->misc->slab_flag);
+        halo_unpack_kernel<T, 3><<<1, 32, 0, g->stream>>>(recv_block, 0u, xyz, nullptr, &g->misc->halo_n, &g->misc->slab_flag);
         g->launches++;
       }
       return ZB_OK;  // misc->halo_n stays 0
     }
     const uint32_t blocks = (uint32_t)((room + 255) / 256);
     if (nd == 3)
-      halo_unpack_kernel<T, 3><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)room, xyz + n_local * 3,
+      halo_unpack_kernel<T, 3><<<blocks, 256, 0, g->stream>>>(recv_block, (uint32_t)room, xyz + n_local * 3,
                                                               static_cast<uint32_t*>(g->halo_labels.p), &g->misc->halo_n,
                                                               &g->misc->slab_flag);
     else
-      halo_unpack_kernel<T, 2><<<blocks, 256, 0, g->stream>>>(static_cast<const T*>(g->halo_recv.p), (uint32_t)room, xyz + n_local * 2,
+      halo_unpack_kernel<T, 2><<<blocks, 256, 0, g->stream>>>(recv_block, (uint32_t)room, xyz + n_local * 2,
                                                               static_cast<uint32_t*>(g->halo_labels.p), &g->misc->halo_n,
                                                               &g->misc->slab_flag);
     g->launches++;
@@ -2013,6 +2137,11 @@ static int slab_collect(zb_grid* g, bool* redone) {
   const uint32_t f2 = g->h_misc->slab_flag;
   g->n_halo = g->h_misc->halo_n;
   g->n = g->n_local + g->n_halo;
+  if (f2 & 8u) {
+    g->built = false;
+    return fail(g, ZB_ERR_CUDA, "a peer did not arrive at an exchange of the slab step within %llu s",
+                (unsigned long long)(kP2pTimeoutNs / 1000000000ull));
+  }
   if (f2 & 2u) {
     g->built = false;
     return fail(g, ZB_ERR_CAPACITY, "the neighbour's top layer exceeds halo_cap = %llu rows (or the spare rows of buf)",
@@ -2050,18 +2179,32 @@ int zb_grid_lj_energy_allreduce(zb_grid* g, int cmp, double filter_cutoff, doubl
   double* red = static_cast<double*>(g->red.p);
   for (int attempt = 0; attempt < 2; ++attempt) {
     int local_rc = g->built ? ZB_OK : ZB_ERR_NOT_BUILT;
-    if (local_rc == ZB_OK)
-      local_rc = g->dtype == ZB_F32 ? lj_impl<float>(g, cmp, filter_cutoff) : lj_impl<double>(g, cmp, filter_cutoff);
-    if (local_rc == ZB_OK) {
-      // (energy, pair count as f64: exact below 2^53, error flag) -> one all-reduce(sum) -> host
-      pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, &g->misc->flags,
-                                                       &g->misc->slab_flag, red);
+    if (g->p2p.ok) {
+      // over peer memory: fold of the per-block partials + verdict + all-reduce in ONE launch behind the LJ kernel
+      uint32_t nblocks = 0;
+      if (local_rc == ZB_OK)
+        local_rc = g->dtype == ZB_F32 ? lj_impl<float>(g, cmp, filter_cutoff, &nblocks) : lj_impl<double>(g, cmp, filter_cutoff, &nblocks);
+      p2p_energy_kernel<<<1, 256, 0, g->stream>>>(g->p2p.peers, N.world, N.rank, ++g->p2p.seq_energy,
+                                                  static_cast<const double*>(g->block_energy.p),
+                                                  static_cast<const unsigned long long*>(g->block_totals.p),
+                                                  local_rc == ZB_OK ? nblocks : 0u, local_rc == ZB_OK ? 0 : 1, &g->misc->flags,
+                                                  &g->misc->slab_flag, &g->misc->energy, &g->misc->pair_total, red);
       g->launches++;
+      ZB_CUDA(cudaGetLastError());
     } else {
-      const double bad[3] = {0.0, 0.0, 1.0};
-      ZB_CUDA(cudaMemcpyAsync(red, bad, sizeof bad, cudaMemcpyHostToDevice, g->stream));
+      if (local_rc == ZB_OK)
+        local_rc = g->dtype == ZB_F32 ? lj_impl<float>(g, cmp, filter_cutoff) : lj_impl<double>(g, cmp, filter_cutoff);
+      if (local_rc == ZB_OK) {
+        // (energy, pair count as f64: exact below 2^53, error flag) -> one all-reduce(sum) -> host
+        pack_energy_count_kernel<<<1, 1, 0, g->stream>>>(&g->misc->energy, &g->misc->pair_total, &g->misc->flags,
+                                                         &g->misc->slab_flag, red);
+        g->launches++;
+      } else {
+        const double bad[3] = {0.0, 0.0, 1.0};
+        ZB_CUDA(cudaMemcpyAsync(red, bad, sizeof bad, cudaMemcpyHostToDevice, g->stream));
+      }
+      ZB_NCCL(N.AllReduce(red, red, 3, ncclDouble, ncclSum, N.comm, g->stream));
     }
-    ZB_NCCL(N.AllReduce(red, red, 3, ncclDouble, ncclSum, N.comm, g->stream));
     ZB_CUDA(cudaMemcpyAsync(g->h_red, red, 3 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
     ZB_CUDA(cudaStreamSynchronize(g->stream));
     if (local_rc != ZB_OK) return local_rc;  // g->err holds this rank's own reason
