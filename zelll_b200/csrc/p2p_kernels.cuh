@@ -24,7 +24,7 @@
 namespace zb {
 
 constexpr int kP2pMaxWorld = 16;
-constexpr unsigned long long kP2pTimeoutNs = 4000000000ull;  // 4 s
+constexpr unsigned long long kP2pTimeoutNs = 20000000000ull;  // 20 s: ranks may reach their first exchange seconds apart
 
 struct __align__(64) P2pSlot {
   double v[6];
