@@ -453,6 +453,49 @@ def run_ours(args):
         ms_e2e, (energy_e, pairs_e), _, _ = timed(step_e2e, steps, drain=drain)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the same step under SUSTAINED load (seconds, not milliseconds): does the burst number hold? ----
+    sustained = None
+    if args.sustained_s > 0:
+        k_sus = max(steps, int(args.sustained_s * 1e3 / max(ms_total / steps, 1e-3)))
+        s2 = ClockSampler(local_rank)
+        if rank == 0:
+            s2.start()
+            time.sleep(0.3)
+        ms_sus, _, _, _ = timed(step_resident, k_sus)
+        c2 = s2.stop() if rank == 0 else None
+        sustained = {"steps": k_sus, "ms_per_step": ms_sus / k_sus, "clocks": c2}
+
+    # ---- f32 grids (benches/lj.rs:11, examples/cachemisses.rs:40-47 make f32 a first-class config): a short
+    # extra leg on rank 0's GPU, outside the headline: rebuild + pair count at the same n, LJ at n = 10^6
+    # (in this box f32 coordinates collide beyond ~10^6 particles: |z| reaches n / 18)
+    f32_leg = None
+    if not distributed and not args.no_f32:
+        def _time(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                out = fn()
+            e1.record(stream)
+            torch.cuda.synchronize(device)
+            return e0.elapsed_time(e1) / reps, out
+
+        p32 = torch.from_numpy(host_pts.astype(np.float32)).to(device)
+        g32 = zelll_b200.CellGrid(p32, CUTOFF, dtype=np.float32, device=local_rank)
+        g32.use_stream(stream.cuda_stream)
+        ms_b, _ = _time(lambda: g32.rebuild_mut(p32, None))
+        ms_c, c32 = _time(lambda: g32.pair_count(CUTOFF, "le"))
+        n_small = min(n_per, 1_000_000)
+        q32 = torch.from_numpy(workload.generate_points_random(n_small, dtype=np.float32)).to(device)
+        g32.rebuild(q32, CUTOFF)
+        ms_l, e32 = _time(lambda: (g32.rebuild_mut(q32, None), g32.lj_energy(CUTOFF, "lt"))[1])
+        f32_leg = {"n": n_per, "rebuild_ms": ms_b, "pair_count_le_ms": ms_c, "pairs_le": int(c32),
+                   "n_lj": n_small, "rebuild_plus_lj_ms": ms_l, "energy_f32": float(e32),
+                   "algorithmic_bytes_per_particle": {"rebuild": 40.8, "lj": 12.8}}
+        del g32, p32, q32
+
     ms_step = ms_total / steps
     ms_step_e2e = ms_e2e / steps
     if rank != 0:
@@ -532,6 +575,10 @@ def run_ours(args):
         "clocks": clocks, "pairs_per_step": total_pairs, "energy": energy,
         "particles_per_s": n_per * world / (ms_step * 1e-3),
     }
+    if sustained is not None:
+        line["sustained"] = sustained
+    if f32_leg is not None:
+        line["f32"] = f32_leg
     if parity is not None:
         line["parity_check"] = parity
     print(json.dumps(line))
@@ -552,6 +599,9 @@ def main():
                     help="presorted = rows sorted by z (examples/cachemisses.rs:57-59, BASELINE.json configs[3])")
     ap.add_argument("--box-xy", type=int, default=3, help="box width in cells along x and y (3 = benches/lj.rs; e.g. 300 for a wide halo)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the pre-timing parity check")
+    ap.add_argument("--sustained-s", type=float, default=2.0,
+                    help="seconds of back-to-back steps timed after the K-step region (reported as `sustained`; 0 = skip)")
+    ap.add_argument("--no-f32", action="store_true", help="skip the f32 leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (very large --n-per-gpu runs)")
     args = ap.parse_args()

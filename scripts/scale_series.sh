@@ -5,9 +5,9 @@ N=$1; TAG=$2; shift 2
 run() {  # name, extra args...
   name=$1; shift
   if [ "$N" = "1" ]; then
-    python bench.py --gpus 1 --steps 10 --warmup 3 "$@" 2> gpurun_out/scale_${TAG}_${name}.err | grep '^{' > gpurun_out/scale_${TAG}_${name}.json
+    python bench.py --gpus 1 --steps 10 --warmup 3 --sustained-s 0 --no-f32 "$@" 2> gpurun_out/scale_${TAG}_${name}.err | grep '^{' > gpurun_out/scale_${TAG}_${name}.json
   else
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus $N --steps 10 --warmup 3 "$@" \
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus $N --steps 10 --warmup 3 --sustained-s 0 "$@" \
       2> gpurun_out/scale_${TAG}_${name}.err | grep '^{' > gpurun_out/scale_${TAG}_${name}.json
   fi
   python - <<PY
