@@ -833,3 +833,30 @@ def test_binary_matches_tracked_sources():
         pytest.skip("experiment build selected with ZB_LIB")
     got = _ffi.load().zb_build_id().decode()
     assert got == "zb-build-id:" + build.source_hash()
+
+
+def test_nan_coordinate_is_never_a_pair(zb):
+    """A NaN coordinate is accepted like upstream (Rust's `as i32` puts it in cell 0 of its axis) and can never
+    pass a distance filter; the prefiltered count kernel must hand such tiles to the exact kernel.  (The
+    bounding box of a cloud with NaNs is order-dependent in a sequential min/max fold, so this is a
+    self-consistency test: every consumer agrees, and the finite particles' pairs are those of the cloud
+    without the NaN rows whenever the box is unchanged.)"""
+    pts, cutoff = _cloud("lj", 5000, np.float64)
+    pts = pts.copy()
+    bad = [17, 4000]
+    pts[17, 1] = np.nan
+    pts[4000, 2] = np.nan
+    cg = zb.CellGrid(pts, cutoff)
+    for cmp in ("lt", "le"):
+        got = canonical_pairs(cg.particle_pairs(cutoff, cmp))
+        assert cg.pair_count(cutoff, cmp) == len(got)       # prefiltered count == exact pair list
+        assert not np.any(np.isin(got, bad))
+        e, m = cg.lj_energy(cutoff, cmp, return_pairs=True)
+        assert m == len(got) and np.isfinite(e)
+    # the same cloud with the NaN rows replaced by far-away-in-cell-space duplicates of a corner: same box
+    ref_pts = np.delete(pts, bad, axis=0)
+    if np.array_equal(ref_pts.min(0), np.nanmin(pts, 0)) and np.array_equal(ref_pts.max(0), np.nanmax(pts, 0)):
+        keep = np.delete(np.arange(len(pts)), bad)
+        ref = zb.CellGrid(ref_pts, cutoff)
+        want = keep[canonical_pairs(ref.particle_pairs(cutoff, "lt")).astype(np.int64)]
+        assert np.array_equal(canonical_pairs(want), canonical_pairs(cg.particle_pairs(cutoff, "lt")))

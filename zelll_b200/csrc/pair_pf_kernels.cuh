@@ -169,6 +169,77 @@ __device__ __forceinline__ void pf_row(const PfStage& st, uint32_t entry, bool v
 }
 
 // ---------------------------------------------------------------------------------------------
+// Count consumer: one chunk of up to 32 NJ candidates, everything specialised by NJ (a cell's last chunk
+// rarely fills four slots; set-up and mask bookkeeping are paid per slot in use).
+template <int CMP, int NJ, class Consumer>
+__device__ __forceinline__ void pf_count_chunk(const CellRuns& r, const PfStage& st, uint32_t kb, const PfThresh& th, double c2,
+                                               Consumer& cons) {
+  const unsigned lane = lane_id();
+  const uint32_t hbl = r.hb - st.plo, hend = hbl + r.m;
+  const uint32_t first_home = r.K - r.m;  // candidates [first_home, K) are the home cell's own particles
+  uint64_t cx[kPfMaxNJ], cy[kPfMaxNJ], cz[kPfMaxNJ];
+  uint32_t posl[NJ], lim[NJ];
+#pragma unroll
+  for (int q = 0; q < NJ; ++q) {
+    const uint32_t k = kb + 32u * q + lane;
+    const bool valid = k < r.K;
+    posl[q] = r.pos(k) - st.plo;
+    lim[q] = valid ? (k >= first_home ? posl[q] : hend) : hbl;
+    float x = kPfIdle, y = kPfIdle, z = kPfIdle;
+    if (valid) {
+      const uint32_t a = st.xf + posl[q] * 4u;
+      x = lds_f32<0>(a);
+      y = lds_f32<kPfOffF>(a);
+      z = lds_f32<2 * kPfOffF>(a);
+    }
+    cx[q] = pk2(x, x);
+    cy[q] = pk2(y, y);
+    cz[q] = pk2(z, z);
+  }
+#pragma unroll 1
+  for (uint32_t b0 = hbl & ~1u; b0 < hend; b0 += 32u) {
+    const uint32_t S = min(16u, (hend - b0 + 1u) >> 1);
+    uint32_t mask[kPfMaxNJ];
+#pragma unroll
+    for (int q = 0; q < kPfMaxNJ; ++q) mask[q] = 0u;
+    int32_t tmin = 0x7fffffff;
+    pf_tests<NJ, true>(st, b0, S, cx, cy, cz, th, mask, tmin);
+    const uint32_t top = b0 + 2u * S - 1u;
+    const uint32_t first = max(hbl, b0);
+    const uint32_t himask = top - first >= 31u ? 0xffffffffu : (2u << (top - first)) - 1u;
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+      const int32_t jlo = (int32_t)(top + 1u) - (int32_t)lim[q];
+      c += __popc(mask[q] & himask & shl_clamp(0xffffffffu, (uint32_t)max(jlo, 0)));
+    }
+    // some t of this lane inside the guard band (taken over ALL its tests, masked-out ones included:
+    // conservative): decide the lane's pairs of this pass in f64
+    const bool amb = tmin <= th.band;
+    if (__any_sync(0xffffffffu, amb)) {
+      if (amb) {
+        c = 0;
+        uint32_t pq[NJ], lq[NJ];
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) { pq[q] = posl[q]; lq[q] = lim[q]; }
+#pragma unroll 1
+        for (int q = 0; q < NJ; ++q) {
+          const uint32_t e = min(lq[0], top + 1u);
+#pragma unroll 1
+          for (uint32_t i = first; i < e; ++i) {
+            double dsq;
+            c += pf_exact<CMP>(st, i, pq[0], c2, dsq) ? 1u : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u + 1 < NJ; ++u) { pq[u] = pq[u + 1]; lq[u] = lq[u + 1]; }
+        }
+      }
+    }
+    cons.add(c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One home cell.  Its K candidates are taken in chunks of up to 128 (lane l holds candidates kb + 32 q + l,
 // q < nj <= 4); only the test loop is specialised by nj, everything around it exists once per kernel
 // (the kernel has to stay small: instruction cache).  `qn` = entries waiting in this warp's queue.
@@ -178,6 +249,17 @@ __device__ __forceinline__ void pf_cell(const CellRuns& r, const PfStage& st, co
   constexpr bool kCount = Consumer::kCountsOnly;
   constexpr int NJ = kPfMaxNJ;
   if (r.m == 0) return;
+  if constexpr (kCount) {
+#pragma unroll 1
+    for (uint32_t kb = 0; kb < r.K; kb += 32u * NJ) {
+      const uint32_t nj = (r.K - kb + 31u) >> 5;
+      if (nj >= 4) pf_count_chunk<CMP, 4>(r, st, kb, th, c2, cons);
+      else if (nj == 3) pf_count_chunk<CMP, 3>(r, st, kb, th, c2, cons);
+      else if (nj == 2) pf_count_chunk<CMP, 2>(r, st, kb, th, c2, cons);
+      else pf_count_chunk<CMP, 1>(r, st, kb, th, c2, cons);
+    }
+    return;
+  }
   const unsigned lane = lane_id();
   const uint32_t hbl = r.hb - st.plo;  // stage-local index of the home cell's first record
   const uint32_t hend = hbl + r.m;
