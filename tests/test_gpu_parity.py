@@ -860,3 +860,14 @@ def test_nan_coordinate_is_never_a_pair(zb):
         ref = zb.CellGrid(ref_pts, cutoff)
         want = keep[canonical_pairs(ref.particle_pairs(cutoff, "lt")).astype(np.int64)]
         assert np.array_equal(canonical_pairs(want), canonical_pairs(cg.particle_pairs(cutoff, "lt")))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,n", [("cube", 60000), ("plane", 40000)])
+def test_wide_grids_row_tiles(zb, kind, n, dtype):
+    """Grids many cells across (a plane of cells holds more records than the stage): tiles are segments of one
+    x-row and the stage takes the five row segments of the half shell.  25^3 cells / 70 x 70 x 2 cells."""
+    pts, cutoff = _cloud(kind, n, dtype)
+    cg, og = _check_against_oracle(zb, pts, cutoff, dtype, 3)
+    shape = cg.info().shape()
+    assert int(shape[0]) * int(shape[1]) + int(shape[0]) + 10 >= 512  # beyond the staged CSR window

@@ -82,6 +82,10 @@ struct PairParams {
   uint32_t home_lo, home_hi;  // cell id range acting as home cells
   uint32_t tile_cells;
   uint32_t ntiles;
+  // wide grids (a plane of cells holds far more records than the stage): tiles are segments of ONE x-row,
+  // row_tiles of them per row (0 = tiles of consecutive cell ids across rows), and the stage holds the five
+  // row segments the half shell needs instead of one contiguous range
+  uint32_t row_tiles;
   uint32_t stage_recs;  // capacity of the record stage buffer
   T c2;                 // squared filter radius, in T (cutoff.powi(2))
   T fc;                 // filter radius
@@ -102,6 +106,20 @@ struct PairParams {
   // csr = ubegin, ukeys[u] = cx + w0 (cy + w1 cz) ascending; neighbour cells are found by binary search
   const unsigned long long* ukeys;
 };
+
+// home cells [c0, c1) of tile t
+__device__ __forceinline__ void tile_cells_of(uint32_t t, uint32_t home_lo, uint32_t home_hi, uint32_t tile_cells,
+                                              uint32_t row_tiles, uint32_t w0, uint32_t& c0, uint32_t& c1) {
+  if (row_tiles) {
+    const uint32_t row = t / row_tiles, seg = t - row * row_tiles;
+    const uint32_t r0 = home_lo + row * w0;
+    c0 = r0 + seg * tile_cells;
+    c1 = min(c0 + tile_cells, r0 + w0);
+  } else {
+    c0 = home_lo + t * tile_cells;
+    c1 = min(c0 + tile_cells, home_hi);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D TMA bulk copy (PTX; SASS: SYNCS / UBLKCP)
@@ -806,13 +824,43 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
     if (threadIdx.x == 0) s_tile[par] = gridDim.x + atomicAdd(p.tile_next, 1u);
     const uint32_t w = p.work_list ? p.work_list[wi] : wi;  // plain loads: written by the launch before this one
     const uint32_t tile = p.tile_list ? __ldg(p.tile_list + w) : w;
-    const uint32_t c0 = p.home_lo + tile * p.tile_cells;
-    const uint32_t c1 = min(c0 + p.tile_cells, p.home_hi);
-    const uint32_t cl = kSparse ? c0 : (c0 > halo ? c0 - halo : 0u);  // (sparse grids: no staged halo, `halo` may have wrapped)
+    uint32_t c0, c1;
+    tile_cells_of(tile, p.home_lo, p.home_hi, p.tile_cells, kSparse ? 0u : p.row_tiles, (uint32_t)p.w0, c0, c1);
+    const bool rows = !kSparse && !kGlobalOnly && p.row_tiles != 0u;  // five row segments instead of one range
+    const uint32_t cl = (kSparse || rows) ? c0 : (c0 > halo ? c0 - halo : 0u);  // (sparse grids: no staged halo, `halo` may have wrapped)
     const uint32_t ncsr = c1 - cl + 1;
-    const uint32_t plo = __ldg(p.csr + cl), phi = __ldg(p.csr + c1);
-    const uint32_t np = phi - plo;
-    const bool staged = !kGlobalOnly && np <= p.stage_recs && ncsr <= (uint32_t)kStageCells;
+    uint32_t plo = __ldg(p.csr + cl);
+    const uint32_t phi = __ldg(p.csr + c1);
+    uint32_t np = phi - plo;
+    // row tiles: the five ranges (A, B, C in the plane below, D the row before, E the home row with its left
+    // neighbour cell), as record ranges [rs[x], re[x]) and their offsets ro[x] in the stage
+    uint32_t rs[5] = {0, 0, 0, 0, 0}, re[5] = {0, 0, 0, 0, 0}, ro[5] = {0, 0, 0, 0, 0};
+    if (rows) {
+      const uint32_t w0 = (uint32_t)p.w0, w1 = (uint32_t)p.w1;
+      const uint32_t row = fast_div(c0, p.div0), cx0 = c0 - row * w0, cx1 = cx0 + (c1 - c0);  // x range [cx0, cx1)
+      const uint32_t cz = fast_div(row, p.div1), cy = row - cz * w1;
+      const uint32_t xa = cx0 > 0 ? cx0 - 1 : 0u, xb = min(cx1 + 1, w0);  // with the x neighbours
+      const uint32_t base = row * w0;
+      auto seg = [&](int x, bool on, uint32_t rbase, uint32_t hi_x) {
+        if (on) {
+          rs[x] = __ldg(p.csr + rbase + xa);
+          re[x] = __ldg(p.csr + rbase + hi_x);
+        }
+      };
+      seg(0, cz > 0 && cy > 0, base - plane - w0, xb);
+      seg(1, cz > 0, base - plane, xb);
+      seg(2, cz > 0 && cy + 1 < w1, base - plane + w0, xb);
+      seg(3, cy > 0, base - w0, xb);
+      seg(4, true, base, cx1);
+      np = 0;
+#pragma unroll
+      for (int x = 0; x < 5; ++x) {
+        ro[x] = np;
+        np += re[x] - rs[x];
+      }
+      plo = 0;  // records are addressed through the per-run offsets below
+    }
+    const bool staged = !kGlobalOnly && np <= p.stage_recs && (rows || ncsr <= (uint32_t)kStageCells);
     // sparse boxes: a tile without home particles has no pairs (its per-tile count stays 0).
     // Staged-only kernel: a tile that does not fit the stage goes to the list of the global-memory launch.
     const bool empty = phi == __ldg(p.csr + c0);
@@ -828,20 +876,36 @@ __global__ void __launch_bounds__(kPairThreads, Consumer::kMinBlocks) pair_kerne
     if (threadIdx.x == 0) s_next = c0 + kPairWarps;
     if (staged) {
       if (threadIdx.x == 0 && np > 0) {
-        const uint32_t bytes = np * (uint32_t)sizeof(Rec<T>);
-        mbar_expect_tx(&s_bar, bytes);
-        bulk_g2s(s_rec, p.sorted + plo, bytes, &s_bar);
+        mbar_expect_tx(&s_bar, np * (uint32_t)sizeof(Rec<T>));
+        if (rows) {
+#pragma unroll
+          for (int x = 0; x < 5; ++x)
+            if (re[x] > rs[x]) bulk_g2s(s_rec + ro[x], p.sorted + rs[x], (re[x] - rs[x]) * (uint32_t)sizeof(Rec<T>), &s_bar);
+        } else {
+          bulk_g2s(s_rec, p.sorted + plo, np * (uint32_t)sizeof(Rec<T>), &s_bar);
+        }
       }
-      for (uint32_t k = threadIdx.x; k < ncsr; k += kPairThreads) s_csr[k] = __ldg(p.csr + cl + k);
-      __syncthreads();
+      if (!rows) {
+        for (uint32_t k = threadIdx.x; k < ncsr; k += kPairThreads) s_csr[k] = __ldg(p.csr + cl + k);
+        __syncthreads();
+      }
     }
     // one thread per home cell computes the cell's run descriptor while the bulk copy is in flight
     {
-      const uint32_t* csrb = staged ? s_csr - cl : p.csr;
+      const uint32_t* csrb = (staged && !rows) ? s_csr - cl : p.csr;
       for (uint32_t k = threadIdx.x; k < c1 - c0; k += kPairThreads) {
         CellRuns r;
         if constexpr (kSparse) cell_runs_sparse(p, c0 + k, r);
         else cell_runs(p, c0 + k, csrb, r);
+        if (rows && staged) {
+          // record index -> stage index: every run lives in its own segment of the stage
+          r.shA += ro[0] - rs[0];
+          r.shB += ro[1] - rs[1];
+          r.shC += ro[2] - rs[2];
+          r.shD += ro[3] - rs[3];
+          r.shE += ro[4] - rs[4];
+          r.hb += ro[4] - rs[4];
+        }
         s_desc[k] = r;
       }
     }
@@ -913,13 +977,13 @@ __global__ void finalize_kernel(const double* __restrict__ block_energy,
 
 // sparse boxes: the tiles whose home cells hold at least one particle (order unspecified)
 __global__ void tile_list_kernel(const uint32_t* __restrict__ csr, uint32_t home_lo, uint32_t home_hi,
-                                 uint32_t tile_cells, uint32_t ntiles, uint32_t* __restrict__ list,
-                                 uint32_t* __restrict__ count) {
+                                 uint32_t tile_cells, uint32_t row_tiles, uint32_t w0, uint32_t ntiles,
+                                 uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = false;
   if (t < ntiles) {
-    const uint32_t c0 = home_lo + t * tile_cells;
-    const uint32_t c1 = min(c0 + tile_cells, home_hi);
+    uint32_t c0, c1;
+    tile_cells_of(t, home_lo, home_hi, tile_cells, row_tiles, w0, c0, c1);
     live = __ldg(csr + c1) != __ldg(csr + c0);
   }
   const unsigned b = __ballot_sync(0xffffffffu, live);

@@ -70,6 +70,7 @@ struct Misc {
 
 struct PairPlan {
   uint32_t tile_cells, ntiles, stage_recs, blocks;
+  uint32_t row_tiles = 0;  // wide grids: tiles are segments of one x-row, this many per row
   size_t smem;        // dynamic shared memory of the kernel that runs first
   bool prefilter;     // f64 grids: pf_pair_kernel first, then the exact kernel over the work items it declined
   uint32_t stage_recs_exact;
@@ -135,7 +136,7 @@ struct zb_grid {
   const void* pf_list_zeroed = nullptr;  // the allocation whose count has been cleared once
   DevBuf tile_list; // sparse boxes: [count, tile ids...] of the tiles with home particles
   uint64_t tile_list_build = ~0ull;  // build_id / tile_cells the list was made for
-  uint32_t tile_list_cells = 0;
+  uint32_t tile_list_cells = 0, tile_list_rows = 0;
   Misc* misc = nullptr;       // device
   Misc* h_misc = nullptr;     // pinned host mirror for small read-backs
   uint32_t pair_ntiles_cap = 0;
@@ -150,6 +151,7 @@ struct zb_grid {
     // Measured neutral on B200 (LJ 1.159 unsplit vs 1.178 ms split at n = 10^7): the 5 k-instruction kernel
     // is not instruction-cache bound, so one launch stays the default.
     bool split = false;
+    bool row_tiles = true;  // ZB_ROW_TILES=0: wide grids read records through L1/L2 instead of staging row segments
     bool slab_spec = true;  // ZB_SLAB_SPEC=0: native slab steps always wait for the box all-reduce
     bool p2p = true;        // ZB_P2P=0: the slab step's exchanges go through NCCL instead of mapped peer memory
     uint32_t p2p_halo_rows = 8192;  // ZB_P2P_HALO_ROWS: rows of the mapped halo blocks
@@ -863,6 +865,22 @@ PairPlan plan_pairs(const zb_grid* g, size_t warp_smem, size_t pf_warp_smem, int
   tc = std::min<uint32_t>(std::max<uint32_t>(tc, 1), kMaxTileCells);
   pl.tile_cells = tc;
   pl.ntiles = nhome ? (nhome + tc - 1) / tc : 0;
+  // Wide grids (cubes, slabs many cells across): a tile plus its lower halo -- a whole plane of cells -- does
+  // not fit the stage as ONE range.  Tiles then become segments of one x-row and the stage takes the five row
+  // segments of the half shell (three in the plane below, the row before, the home row): 5 (T + 2) cells.
+  pl.row_tiles = 0;
+  if (!g->sparse && !pl.prefilter && g->tune.row_tiles && halo + 1 + 8 >= (uint64_t)kStageCells && nhome && !g->tune.tile_cells) {
+    const uint32_t w0 = (uint32_t)g->wshape[0];
+    const double fit = 0.8 * pl.stage_recs_exact / (5.0 * std::max(ppc, 0.25)) - 2.0;
+    if (fit >= 4.0) {
+      uint32_t seg = std::min<uint32_t>({(uint32_t)fit, w0, (uint32_t)kMaxTileCells});
+      const uint32_t per_row = (w0 + seg - 1) / seg;
+      seg = (w0 + per_row - 1) / per_row;  // equal segments
+      pl.row_tiles = per_row;
+      pl.tile_cells = seg;
+      pl.ntiles = (nhome / w0) * per_row;
+    }
+  }
   pl.blocks = (uint32_t)g->sm_count * kMaxPairCtasPerSm * 2;  // upper bound (buffers): both launches of a prefiltered pass
   pl.smem_exact = (size_t)pl.stage_recs_exact * sizeof(Rec<T>) + kMaxTileCells * sizeof(CellRuns) +
                   (kStageCells + 4) * sizeof(uint32_t) + kPairWarps * warp_smem;
@@ -893,6 +911,7 @@ PairParams<T> pair_params(zb_grid* g, const PairPlan& pl, double filter_cutoff) 
   p.home_hi = g->home_hi;
   p.tile_cells = pl.tile_cells;
   p.ntiles = pl.ntiles;
+  p.row_tiles = pl.row_tiles;
   p.stage_recs = pl.stage_recs;
   p.fb_list = nullptr;
   p.fb_count = nullptr;
@@ -922,14 +941,15 @@ int sparse_tile_list(zb_grid* g, const PairPlan& pl, PairParams<T>& p) {
   if (pl.ntiles < 4096 || g->n * 8 > (uint64_t)g->ncells) return ZB_OK;
   ZB_TRY(reserve(g, g->tile_list, ((size_t)pl.ntiles + 1) * 4));
   uint32_t* buf = static_cast<uint32_t*>(g->tile_list.p);
-  if (g->tile_list_build != g->build_id || g->tile_list_cells != pl.tile_cells) {
+  if (g->tile_list_build != g->build_id || g->tile_list_cells != pl.tile_cells || g->tile_list_rows != pl.row_tiles) {
     ZB_CUDA(cudaMemsetAsync(buf, 0, 4, g->stream));
     tile_list_kernel<<<(pl.ntiles + 255) / 256, 256, 0, g->stream>>>(csr_ptr(g), g->home_lo, g->home_hi, pl.tile_cells,
-                                                                 pl.ntiles, buf + 1, buf);
+                                                                 pl.row_tiles, (uint32_t)g->wshape[0], pl.ntiles, buf + 1, buf);
     g->launches++;
     ZB_CUDA(cudaGetLastError());
     g->tile_list_build = g->build_id;
     g->tile_list_cells = pl.tile_cells;
+    g->tile_list_rows = pl.row_tiles;
     // the list is filled in atomic arrival order: per-work-item counts of an earlier list are void
     g->emit_cache_valid = false;
   }
@@ -1099,7 +1119,8 @@ int lj_impl(zb_grid* g, int cmp, double fc, uint32_t* blocks_out = nullptr) {
 template <class T>
 int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev) {
   // per-tile arrays are indexed by work item: all tiles, or (sparse boxes) the listed ones
-  const bool sparse = g->tile_list_build == g->build_id && g->tile_list_cells == pl.tile_cells && g->tile_list.p &&
+  const bool sparse = g->tile_list_build == g->build_id && g->tile_list_cells == pl.tile_cells &&
+                      g->tile_list_rows == pl.row_tiles && g->tile_list.p &&
                       !(pl.ntiles < 4096 || g->n * 8 > (uint64_t)g->ncells);
   tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), pl.ntiles,
                                                  sparse ? static_cast<const uint32_t*>(g->tile_list.p) : nullptr,
@@ -1176,6 +1197,7 @@ int zb_grid_create(int dtype, int ndim, int device, zb_grid** out) {
   if (const char* e = getenv("ZB_SPLIT")) g->tune.split = atoi(e) != 0;
   if (const char* e = getenv("ZB_SPARSE")) g->tune.sparse = atoi(e);
   if (const char* e = getenv("ZB_SLAB_SPEC")) g->tune.slab_spec = atoi(e) != 0;
+  if (const char* e = getenv("ZB_ROW_TILES")) g->tune.row_tiles = atoi(e) != 0;
   if (const char* e = getenv("ZB_P2P")) g->tune.p2p = atoi(e) != 0;
   if (const char* e = getenv("ZB_P2P_HALO_ROWS")) {
     const long v = atol(e);
