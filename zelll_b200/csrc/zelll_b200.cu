@@ -1845,6 +1845,17 @@ static int p2p_setup(zb_grid* g) {
   auto& N = g->nccl;
   auto& P = g->p2p;
   P.ok = false;
+  // a second zb_comm_init on the same handle: drop the previous communicator's mappings first
+  for (void*& o : P.opened)
+    if (o) {
+      cudaIpcCloseMemHandle(o);
+      o = nullptr;
+    }
+  if (P.local) {
+    cudaFree(P.local);
+    P.local = nullptr;
+  }
+  g->slab = zb_grid::SlabStep{};
   if (N.world < 2) return ZB_OK;
   int ok = (g->tune.p2p && N.world <= kP2pMaxWorld && N.AllGather) ? 1 : 0;
   P.halo_rows = g->tune.p2p_halo_rows;
