@@ -435,7 +435,12 @@ def test_reference_sdf_golden(zb, golden):
 # ---------------------------------------------------------------------------------------------
 # real multi-GPU run (NCCL) when the box has more than one GPU; the host logic is covered on CPU by
 # tests/test_sharded_cpu.py (gloo) and the per-rank engine by test_sharded_union_equals_single_grid
-def test_distributed_nccl_matches_single_gpu():
+@pytest.mark.parametrize("transport", ["peer-memory+speculation", "nccl+wait"])
+def test_distributed_nccl_matches_single_gpu(transport):
+    """scripts/dist_check.py under torchrun (needs >= 2 GPUs): general, slab-local and native slab paths, then
+    repeated and moved frames through the native path -- once with the default transport (exchanges over
+    mapped peer memory, speculative box) and once with NCCL collectives and a wait for the box."""
+    import os
     import subprocess
     import sys
 
@@ -448,9 +453,12 @@ def test_distributed_nccl_matches_single_gpu():
     root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", "scripts/dist_check.py", "200000"]
-    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if transport == "nccl+wait":
+        env.update(ZB_P2P="0", ZB_SLAB_SPEC="0")
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "MISMATCH" not in out.stdout
+    assert "MISMATCH" not in out.stdout and out.stdout.count("-> OK") >= 8
 
 
 # ---------------------------------------------------------------------------------------------
