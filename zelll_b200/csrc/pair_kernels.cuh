@@ -661,22 +661,40 @@ __device__ __forceinline__ bool cell_runs_sparse(const PairParams<T>& p, uint32_
   const unsigned long long key = __ldg(p.ukeys + u);
   const unsigned long long cx = key % w0, row = key / w0, cy = row % w1, cz = row / w1;
   const unsigned long long xl = cx > 0 ? 1u : 0u, xr = (cx + 1 < w0) ? 1u : 0u;
-  // records of the cells with keys [k0, k1] among the compact cells before u
-  auto range = [&](unsigned long long k0, unsigned long long k1, uint32_t& s, uint32_t& l) {
-    const uint32_t lo = lower_bound_ukeys(p.ukeys, u, k0);
+  // records of the cells with keys [k0, k1] among the compact cells before `hi` (<= u).  The wanted cells
+  // sit a row or a plane of NON-EMPTY cells before u, usually far fewer than u itself: gallop backwards from
+  // `hi` to bracket k0, then bisect inside the bracket.  Returns the first compact cell >= k0 so that the
+  // next (smaller-keyed) run can start its search there.
+  auto range = [&](uint32_t hi, unsigned long long k0, unsigned long long k1, uint32_t& s, uint32_t& l) -> uint32_t {
+    uint32_t lo = hi, step = 1;
+    while (lo > 0) {
+      const uint32_t probe = lo > step ? lo - step : 0u;
+      if (__ldg(p.ukeys + probe) < k0) {  // bracket found: first cell >= k0 lies in (probe, lo]
+        const uint32_t first = probe + 1 + lower_bound_ukeys(p.ukeys + probe + 1, lo - probe - 1, k0);
+        lo = first;
+        goto found;
+      }
+      lo = probe;
+      step <<= 1;
+    }
+    lo = 0;  // every cell before hi has a key >= k0
+  found:
     uint32_t up = lo;
-    while (up < u && up < lo + 3u && __ldg(p.ukeys + up) <= k1) ++up;
+    while (up < hi && up < lo + 3u && __ldg(p.ukeys + up) <= k1) ++up;
     s = __ldg(p.csr + lo);
     l = __ldg(p.csr + up) - s;
+    return lo;
   };
   uint32_t sA = 0, lA = 0, sB = 0, lB = 0, sC = 0, lC = 0, sD = 0, lD = 0;
+  // runs in descending key order (D, C, B, A), each search bounded by the previous run's position
+  uint32_t hi = u;
+  if (cy > 0) hi = range(hi, key - w0 - xl, key - w0 + xr, sD, lD);
   if (cz > 0) {
     const unsigned long long kb = key - w0 * w1;  // same (cx, cy), plane below
-    if (cy > 0) range(kb - w0 - xl, kb - w0 + xr, sA, lA);
-    range(kb - xl, kb + xr, sB, lB);
-    if (cy + 1 < w1) range(kb + w0 - xl, kb + w0 + xr, sC, lC);
+    if (cy + 1 < w1) hi = range(hi, kb + w0 - xl, kb + w0 + xr, sC, lC);
+    hi = range(hi, kb - xl, kb + xr, sB, lB);
+    if (cy > 0) hi = range(hi, kb - w0 - xl, kb - w0 + xr, sA, lA);
   }
-  if (cy > 0) range(key - w0 - xl, key - w0 + xr, sD, lD);
   const uint32_t sE = (xl && u > 0 && __ldg(p.ukeys + u - 1) == key - 1) ? __ldg(p.csr + u - 1) : hb, lE = he - sE;
   r.o1 = lA; r.o2 = r.o1 + lB; r.o3 = r.o2 + lC; r.o4 = r.o3 + lD; r.K = r.o4 + lE;
   r.shA = sA; r.shB = sB - r.o1; r.shC = sC - r.o2; r.shD = sD - r.o3; r.shE = sE - r.o4;
