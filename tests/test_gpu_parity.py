@@ -657,8 +657,8 @@ def test_gridcell_views_reference_counts(zb, golden):
     assert cg2.query(pts2.max(0) + 5.0 * g2["cutoff"]) is None
 
 
-@pytest.mark.parametrize("mask", ["7", "0"])
-def test_prefilter_modes_are_bit_exact(mask):
+@pytest.mark.parametrize("mask,split", [("7", "0"), ("0", "0"), ("0", "1")])
+def test_prefilter_modes_are_bit_exact(mask, split):
     """ZB_PREFILTER=<mask> selects which consumers of an f64 grid run through the f32 guard-band prefilter
     kernel (pair_pf_kernels.cuh; default: count only).  With every consumer on it (7) and with none (0) the
     pair sets, counts and energies must be the oracle's.  Run in a subprocess because the switch is read
@@ -697,7 +697,8 @@ cg = zelll_b200.CellGrid(grid, 1.0); og = oracle.OracleCellGrid(grid, 1.0)
 assert cg.pair_count(1.0, "le") == og.pair_count(oracle.CMP_LE, 1.0) > cg.pair_count(1.0, "lt") == og.pair_count(oracle.CMP_LT, 1.0)
 print("prefilter ok")
 """ % root
-    env = dict(os.environ, ZB_PREFILTER=mask)
+    # split = "1": the exact kernel as two launches (staged tiles, then the tiles that did not fit: ZB_SPLIT)
+    env = dict(os.environ, ZB_PREFILTER=mask, ZB_SPLIT=split)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "prefilter ok" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
 
