@@ -61,6 +61,10 @@ constexpr int kMaxNJ = 4;  // candidates held in registers per lane (register ti
 #define ZB_LJ_FUSE 2  // home particles per LJ compaction step (measured: 2 = 3 > 4 > 1)
 #endif
 constexpr int kPairWarps = kPairThreads / 32;
+#ifndef ZB_TAIL_SPLIT
+#define ZB_TAIL_SPLIT 16
+#endif
+constexpr uint32_t kTailSplit = ZB_TAIL_SPLIT;  // a remainder of up to this many candidates is packed (24 = split 17..24 into 16 + <= 8: measured neutral)
 constexpr int kStageCells = 512;  // staged CSR entries per tile (cells + halo + 1)
 constexpr int kMaxTileCells = 128;  // home cells per tile (their descriptors are staged)
 
@@ -792,10 +796,11 @@ __device__ __forceinline__ void process_cell(const CellRuns& r, const Recs recb,
     if (NJMAX >= 2 && rem > 48) {          // two full-ish slots: one broadcast load per 2 tests
       process_group<T, CMP, 2, 1>(r, recb, kb, c2, cons);
       kb += 64;
-    } else if (rem > 16) {                 // one slot (a 33..48 remainder leaves a packed tail behind)
+    } else if (rem > kTailSplit) {         // one slot (a 33..48 remainder leaves a packed tail behind)
       process_group<T, CMP, 1, 1>(r, recb, kb, c2, cons);
       kb += 32;
-    } else if (rem > 8) {                  // <= 16 candidates: two phases of 16 lanes
+    } else if (rem > 8) {                  // two phases of 16 lanes: <= 16 candidates, or the first 16 of 17..24
+                                           // (then <= 8 are left for four phases: 0.75 m iterations instead of m)
       process_group<T, CMP, 1, 2>(r, recb, kb, c2, cons);
       kb += 16;
     } else {                               // <= 8 candidates: four phases of 8 lanes
