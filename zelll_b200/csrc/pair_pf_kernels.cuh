@@ -1,4 +1,5 @@
-// pair_pf_kernels.cuh -- the f64 pair pass with an f32 prefilter (the default for f64 grids).
+// pair_pf_kernels.cuh -- the f64 pair pass with an f32 prefilter (default for the pair COUNT of f64 grids;
+// ZB_PREFILTER selects the consumers, DESIGN.md section 5b has the measurements behind that default).
 //
 // Same enumeration as pair_kernels.cuh (GridCell::particle_pairs, iters.rs:238-241: z-major half shell =
 // 5 runs of consecutive records per home cell, one warp per home cell, lanes = candidates), same
