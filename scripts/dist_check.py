@@ -105,6 +105,32 @@ def main():
         if rank == 0:
             print(f"[dist_check] world={world} frame {k}: pairs {m} vs {m_ref}, energy rel diff {abs(e - e_ref) / abs(e_ref):.2e}, "
                   f"rows incl. halo {n_here} -> {'OK' if good else 'MISMATCH'}")
+    # f32 grids through the native path (halo rows travel as 4 x f32): counts exact, energy to 1e-5
+    n32 = min(n, 100_000)  # f32 coordinates collide in longer boxes (|z| reaches n / 18)
+    p32 = workload.generate_points_random(n32, dtype=np.float32)
+    ref = zelll_b200.CellGrid(p32, cutoff, dtype=np.float32, device=local)
+    e_ref, m_ref = ref.lj_energy(cutoff, "lt", return_pairs=True)
+    c_ref = ref.pair_count(cutoff, "le")
+    ng32 = NativeSlabGrid(dtype=np.float32, device=local)
+    order = np.argsort(p32[:, 2], kind="stable")
+    spts = p32[order]
+    inf_z = spts[0, 2]
+    layer = np.floor((spts[:, 2] - inf_z) / np.float32(cutoff)).astype(np.int64)
+    nz = int(layer.max()) + 1
+    zb, ze = slab_bounds(nz, world, rank)
+    sel = np.nonzero((layer >= zb) & (layer < ze))[0]
+    buf = torch.zeros((len(sel) + 4096, 3), dtype=torch.float32, device=dev)
+    buf[: len(sel)] = torch.from_numpy(spts[sel]).to(dev)
+    for k in range(2):  # the second pass runs speculatively
+        ng32.rebuild_slab_local(buf, len(sel), cutoff, label_offset=int(sel[0]) if len(sel) else 0)
+        e, m = ng32.lj_energy_allreduce(cutoff, "lt", return_pairs=True)
+        ct = torch.tensor([ng32.pair_count(cutoff, "le")], dtype=torch.int64, device=dev)
+        dist.all_reduce(ct)
+        good = m == m_ref and int(ct.item()) == c_ref and abs(e - e_ref) <= 1e-5 * abs(e_ref)
+        ok &= bool(good)
+        if rank == 0:
+            print(f"[dist_check] world={world} f32 pass {k}: pairs {m} vs {m_ref}, le-count {int(ct.item())} vs {c_ref}, "
+                  f"energy rel diff {abs(e - e_ref) / abs(e_ref):.2e} -> {'OK' if good else 'MISMATCH'}")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
