@@ -187,6 +187,22 @@ __device__ __forceinline__ float ld_shared<float>(uint32_t a) {
   return v;
 }
 
+// packed f32x2 arithmetic (sm_100: one FFMA2 = two IEEE fused multiply-adds, half the issue slots of two scalar
+// instructions at the same pipe throughput).  fma(a, 1, b) and fma(a, a, 0) are the correctly rounded sum and
+// product, so the reference's separately rounded f32 arithmetic can be expressed with them bit for bit.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 // lj (benches/lj.rs:42-47): dsq.recip().powi(3) -> (r*r)*r ; 4*t*(t-1).  Exact IEEE division.
 template <class T>
 __device__ __forceinline__ T lj_term(T dsq) {
@@ -743,6 +759,66 @@ __device__ __forceinline__ void exact_tests(const Recs home, uint32_t m, uint32_
   for (int f = 0; f < F; ++f)
 #pragma unroll
     for (int q = 0; q < NJ; ++q) ljf[f * NJ + q] = lj[q];
+  // f32 grids: two tests per packed instruction -- the two candidates of a lane (NJ = 2) or the two fused
+  // home particles (NJ = 1, F = 2).  Same arithmetic, same roundings: (dx*dx + dy*dy) + dz*dz per element.
+  constexpr bool kPacked = sizeof(T) == 4 && CMP != 0 && (NJ == 2 || (NJ == 1 && F == 2));
+  if constexpr (kPacked) {
+    const uint64_t one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f), zero2 = pk2(0.0f, 0.0f);
+    uint64_t cx, cy, cz;  // NJ = 2: the lane's candidate pair
+    if (NJ == 2) {
+      cx = pk2((float)xj[0], (float)xj[NJ - 1]);
+      cy = pk2((float)yj[0], (float)yj[NJ - 1]);
+      cz = pk2((float)zj[0], (float)zj[NJ - 1]);
+    }
+    auto dsq2 = [&](uint64_t ax, uint64_t ay, uint64_t az, uint64_t bx, uint64_t by, uint64_t bz, float& d0, float& d1) {
+      const uint64_t dx = ffma2(bx, mone2, ax), dy = ffma2(by, mone2, ay), dz = ffma2(bz, mone2, az);  // a - b
+      const uint64_t sx = ffma2(dx, dx, zero2), sy = ffma2(dy, dy, zero2), sz = ffma2(dz, dz, zero2);
+      const uint64_t s = ffma2(ffma2(sx, one2, sy), one2, sz);
+      uint32_t u0, u1;
+      unpk2(s, u0, u1);
+      d0 = __uint_as_float(u0);
+      d1 = __uint_as_float(u1);
+    };
+#pragma unroll Consumer::kUnroll
+    for (uint32_t ib = 0; ib < m; ib += F * P) {
+      bool h[NJ * F];
+      T dsq[NJ * F];
+      uint32_t lif[NJ * F];
+      float xi[F], yi[F], zi[F];
+      uint32_t idx[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        uint32_t li;
+        T x, y, z;
+        idx[f] = (P == 1 ? ib : ib + ph) + f * P;
+        home.template load<Consumer::kNeedLabels>(idx[f], x, y, z, li);
+        xi[f] = (float)x; yi[f] = (float)y; zi[f] = (float)z;
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) lif[f * NJ + q] = li;
+      }
+      if (NJ == 2) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          float d0, d1;
+          dsq2(pk2(xi[f], xi[f]), pk2(yi[f], yi[f]), pk2(zi[f], zi[f]), cx, cy, cz, d0, d1);
+          dsq[f * NJ] = (T)d0;
+          dsq[f * NJ + NJ - 1] = (T)d1;
+        }
+      } else {
+        float d0, d1;
+        dsq2(pk2(xi[0], xi[F - 1]), pk2(yi[0], yi[F - 1]), pk2(zi[0], zi[F - 1]), pk2((float)xj[0], (float)xj[0]),
+             pk2((float)yj[0], (float)yj[0]), pk2((float)zj[0], (float)zj[0]), d0, d1);
+        dsq[0] = (T)d0;
+        dsq[NJ * F - 1] = (T)d1;
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) h[f * NJ + q] = idx[f] < thr[q] && passes<CMP>(dsq[f * NJ + q], c2);
+      cons.template test_n<NJ * F>(h, dsq, lif, ljf);
+    }
+    return;
+  }
 #pragma unroll Consumer::kUnroll
   for (uint32_t ib = 0; ib < m; ib += F * P) {
     bool h[NJ * F];

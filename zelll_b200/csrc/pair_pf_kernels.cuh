@@ -53,19 +53,6 @@ constexpr float kPfMaxRel = 1.0e15f;  // |relative coordinate| beyond this (or N
 constexpr uint32_t kPfQueueCap = kPfStageRecs * (uint32_t)sizeof(Rec<double>) / 4u / kPairWarps;  // entries per warp
 static_assert(kPfStageRecs % 8 == 0 && kPfQueueCap >= 256, "stage size");
 
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpk2(uint64_t v, uint32_t& lo, uint32_t& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 // shared-memory loads at (address register + compile-time byte offset)
 template <uint32_t OFF>
 __device__ __forceinline__ uint64_t lds_b64(uint32_t a) {
