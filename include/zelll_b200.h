@@ -221,7 +221,10 @@ int zb_grid_pair_count(zb_grid* g, int cmp, double filter_cutoff, uint64_t* out)
 
 /* Materialised particle_pairs(): `ij` receives n_out rows (label_home, label_neighbor) of
  * uint32 (interleaved; host or device).  Row order is unspecified, as upstream (iters.rs:251).
- * If cap < needed: ZB_ERR_CAPACITY, *n_out = needed, nothing written. */
+ * ij == NULL or cap == 0 is a sizing call: *n_out = rows needed (ZB_ERR_CAPACITY unless that is 0).
+ * A DEVICE buffer is filled in one pass over the pairs, without a counting pass in front of it; if it turns
+ * out too small: ZB_ERR_CAPACITY, *n_out = needed, and the buffer's contents are unspecified.  A host buffer
+ * that is too small is left untouched. */
 int zb_grid_pairs(zb_grid* g, int cmp, double filter_cutoff, uint32_t* ij, uint64_t cap,
                   uint64_t* n_out);
 

@@ -692,6 +692,9 @@ for n, kind in ((20000, "lj"), (6000, "cube"), (4000, "dense")):
         assert m == mo and abs(e - e64) <= 1e-10 * abs(e64), (kind, cmp, e, e64)
     # a filter radius below the cell size, and pairs exactly at the threshold
     assert np.array_equal(oracle.canonical_pairs(cg.particle_pairs(0.37 * c, "le")), og.pairs_canonical(oracle.CMP_LE, 0.37 * c))
+    cg.rebuild(pts, c)   # single-pass list into a device buffer with head-room (nothing sized on this build)
+    dev = cg.particle_pairs_device(c, "lt", capacity=len(og.pairs_canonical(oracle.CMP_LT, c)) + 3000)
+    assert np.array_equal(oracle.canonical_pairs(dev.cpu().numpy().view(np.uint32).reshape(-1, 2)), og.pairs_canonical(oracle.CMP_LT, c))
 grid = np.stack(np.meshgrid(*[np.arange(6.0)] * 3, indexing="ij"), -1).reshape(-1, 3)   # distances exactly 1
 cg = zelll_b200.CellGrid(grid, 1.0); og = oracle.OracleCellGrid(grid, 1.0)
 assert cg.pair_count(1.0, "le") == og.pair_count(oracle.CMP_LE, 1.0) > cg.pair_count(1.0, "lt") == og.pair_count(oracle.CMP_LT, 1.0)
@@ -805,6 +808,65 @@ def test_stable_cell_storage_matches_reference_order(zb):
         assert np.array_equal(cg.cell_storage()[0], labels)   # reproducible layout
         _, e64, _ = og.lj_energy(CMP_LT, cutoff)
         assert abs(e1 - e64) <= F64_RTOL * abs(e64)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_pair_list_single_pass_into_device_buffer(zb, dtype):
+    """A DEVICE destination with a caller-chosen capacity is filled in ONE pass (no counting pass): output slots
+    of 1024 rows, holes closed afterwards (EmitConsumer / emit_fix_* kernels).  The list must be the oracle's for
+    capacities that are exact, barely larger, not a multiple of the slot size and far too large; a capacity that
+    is too small reports the rows needed."""
+    import torch
+    from zelll_b200 import _ffi
+
+    for kind, n in (("lj", 20000), ("cube", 6000), ("dense", 4000), ("clusters", 3000), ("lj", 33), ("lj", 2), ("lj", 0)):
+        pts, cutoff = _cloud(kind, n, dtype) if n else (np.zeros((0, 3), dtype=dtype), 10.0)
+        og = OracleCellGrid(pts, cutoff, dtype=dtype)
+        cg = zb.CellGrid(pts, cutoff, dtype=dtype)
+        for cmp in ("none", "lt", "le"):
+            want = og.pairs_canonical(OCMP[cmp], cutoff)
+            m = len(want)
+            for cap in (m + 5000, m, m + 1, 4 * m + 7):
+                cg.rebuild(pts, cutoff)  # a new build: nothing is known about the list's length
+                got = cg.particle_pairs_device(cutoff, cmp, capacity=cap)
+                assert got.shape[0] == m, (kind, n, cmp, cap, got.shape[0], m)
+                rows = got.cpu().numpy().view(np.uint32).reshape(-1, 2)
+                assert np.array_equal(canonical_pairs(rows), want), (kind, n, cmp, cap)
+            if m > 1:
+                cg.rebuild(pts, cutoff)
+                with pytest.raises(zb.ZelllB200Error) as e:
+                    cg.particle_pairs_device(cutoff, cmp, capacity=m - 1)
+                assert e.value.status == _ffi.ERR_CAPACITY and str(m) in str(e.value)
+                with pytest.raises(zb.ZelllB200Error) as e:  # far too small: most slots are never written
+                    cg.particle_pairs_device(cutoff, cmp, capacity=max(1, m // 7))
+                assert e.value.status == _ffi.ERR_CAPACITY and str(m) in str(e.value)
+                # the handle keeps working, and a sized fetch is exact
+                assert np.array_equal(canonical_pairs(cg.particle_pairs(cutoff, cmp)), want)
+    torch.cuda.synchronize()
+
+
+def test_pair_list_full_size_single_pass(zb):
+    """n = 10^7: 1.6e8 rows written in one pass into a buffer with head-room.  Size-independent properties that
+    pin the set: as many rows as the exact count, all rows distinct, every row a pair inside the cutoff."""
+    import torch
+
+    n = 10_000_000
+    pts = workload.generate_points_random(n)
+    cg = zb.CellGrid(pts, 10.0)
+    rows = cg.particle_pairs_device(10.0, "lt", capacity=17 * n)
+    m = cg.pair_count(10.0, "lt")
+    assert rows.shape[0] == m
+    i = rows[:, 0].to(torch.int64) & 0xFFFFFFFF
+    j = rows[:, 1].to(torch.int64) & 0xFFFFFFFF
+    assert int(i.max()) < n and int(j.max()) < n and bool((i != j).all())
+    key = (torch.minimum(i, j) << 32) | torch.maximum(i, j)
+    key = torch.sort(key).values
+    assert bool((key[1:] != key[:-1]).all())
+    del key
+    x = torch.from_numpy(pts).to(rows.device)
+    d = x[i] - x[j]
+    dsq = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+    assert bool((dsq < 100.0).all())
 
 
 def test_stage_profile_mask_and_rebuild_mut_shrinking_box(zb):

@@ -338,9 +338,31 @@ __device__ __forceinline__ float prefilter_delta(float R_over_fc) {
 // Consumers.  test_n() is called by all 32 lanes of a warp in convergence, once per (fused) home particle
 // step with the candidates a lane holds; hit() is the hand-over point of pf_pair_kernel.
 
+// EmitConsumer's output description (explained there)
+#ifndef ZB_EMIT_CHUNK
+#define ZB_EMIT_CHUNK 512
+#endif
+constexpr uint32_t kEmitChunk = ZB_EMIT_CHUNK;  // rows per output slot (a multiple of 32)
+constexpr uint32_t kEmitNoSlot = 0xffffffffu;
+
+struct EmitOut {
+  uint2* out;
+  uint2* spill;
+  uint32_t out_chunks, spill_chunks;
+  unsigned long long* cursor;  // slots handed out
+  uint2* partial;              // (slot, rows used) of partly filled slots
+  uint32_t* npartial;
+  uint32_t partial_cap;
+  __device__ __forceinline__ uint2* rows(uint32_t slot) const {
+    if (slot < out_chunks) return out + (size_t)slot * kEmitChunk;
+    slot -= out_chunks;
+    return slot < spill_chunks ? spill + (size_t)slot * kEmitChunk : nullptr;
+  }
+};
+
 struct ConsumerSmem {
   unsigned long long tile_count;  // CountConsumer
-  uint32_t cursor;                // EmitConsumer
+  EmitOut emit;                   // EmitConsumer: the fields of its Args that only the rare paths need
 };
 
 // -- count -----------------------------------------------------------------------------------
@@ -398,15 +420,27 @@ struct CountConsumer {
 };
 
 // -- emit ------------------------------------------------------------------------------------
-// Each tile owns the output range [tile_offsets[tile], tile_offsets[tile+1]) computed from a
-// previous CountConsumer pass, so the list is compact and needs no global atomics: warps stage
-// hits in a shared queue and claim slots 32 at a time from the tile's shared cursor.
+// ONE pass, no sizing pass in front of it.  The output is handed out in SLOTS of kEmitChunk rows from one
+// global cursor, one slot per WARP at a time: a warp writes its 32-row stores into its own slot without any
+// atomic, and fetches the slot after ahead of need (the atomic's result is first looked at when the current
+// slot is full, thousands of cycles later).  One global atomic per kEmitChunk rows -- a same-address atomic per
+// 32-row store (5e6 of them at n = 1e7) would serialise in L2, and slots shared by the warps of a CTA cost
+// ~0.9 us of CTA time per slot switch (measured: 1.85 ms at 1024-row slots, 2.8 ms at 256).
+// Slots [0, out_chunks) are the caller's buffer, the next spill_chunks a scratch area (a pass needs up to two
+// slots per warp more than the list is long).  Every warp ends with at most two partly filled slots (its
+// current one and the one it fetched ahead); they are recorded in `partial` and the emit_fix_* kernels below
+// close the holes (order is unspecified upstream, iters.rs:251, so rows may move): full slots from behind the
+// end of the list move into the partial slots in front of it, the partial rows are packed behind the last
+// full slot.  A list longer than the capacity keeps counting slots without writing, so the caller still
+// learns the size it needs.
+__device__ __noinline__ uint2* emit_spill_rows(const ConsumerSmem* cs, uint32_t slot) {
+  slot -= cs->emit.out_chunks;
+  return slot < cs->emit.spill_chunks ? cs->emit.spill + (size_t)slot * kEmitChunk : nullptr;
+}
+
 template <class T>
 struct EmitConsumer {
-  struct Args {
-    const unsigned long long* tile_offsets;  // [ntiles + 1]
-    uint2* out;
-  };
+  using Args = EmitOut;
   static constexpr int kWarpSmemBytes = (32 + 32 * kMaxNJ * 2) * sizeof(uint2);  // one row + one fused step
   static constexpr int kPfWarpSmemBytes = 64 * sizeof(uint2);  // pf_pair_kernel hands over one row at a time
   static constexpr int kStage = 5;  // ZB_STAGE_PAIR_EMIT
@@ -415,34 +449,47 @@ struct EmitConsumer {
   static constexpr int kUnroll = 2;
   static constexpr int kFuse = 2;
   static constexpr int kMinBlocks = ZB_PAIR_MINBLOCKS;
-  Args a;
+  // only what the 32-row store needs lives in registers; the rest of Args waits in shared memory (cs->emit)
+  uint2* out;
+  uint32_t out_chunks;
   ConsumerSmem* cs;
-  uint2* q;        // (label, label) rows waiting for a full 32-row store
+  uint2* q;        // (label, label) rows waiting for a full 32-row store; survives tile changes
   uint32_t qn;
   unsigned ltmask;
-  unsigned long long base;
+  uint32_t slot, used;  // this warp's output slot and the rows of it that are written
+  uint32_t next_l0;     // lane 0: the slot fetched ahead
+  bool has_next;
 
-  __device__ EmitConsumer(const Args& args, ConsumerSmem* s, void* warp_smem, T)
-      : a(args), cs(s), q(static_cast<uint2*>(warp_smem)), qn(0), ltmask(lanemask_lt()), base(0) {}
-  __device__ __forceinline__ void tile_begin(uint32_t tile, const Rec<T>*, bool) {
-    if (threadIdx.x == 0) cs->cursor = 0;
-    base = a.tile_offsets[tile];
-    qn = 0;
+  __device__ static __forceinline__ uint32_t fetch_slot(unsigned long long* cursor) {
+    uint32_t v = 0;
+    if (lane_id() == 0) v = (uint32_t)atomicAdd(cursor, 1ull);
+    return v;
   }
-  // write the rows for which `h` holds to the tile's output range
-  __device__ __forceinline__ void put(bool h, uint2 row) {
-    const unsigned b = __ballot_sync(0xffffffffu, h);
-    if (b == 0) return;
-    uint32_t pos = 0;
-    if (lane_id() == 0) pos = atomicAdd(&cs->cursor, (uint32_t)__popc(b));
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    if (h) a.out[base + pos + __popc(b & ltmask)] = row;
+  __device__ EmitConsumer(const Args& args, ConsumerSmem* s, void* warp_smem, T)
+      : out(args.out), out_chunks(args.out_chunks), cs(s), q(static_cast<uint2*>(warp_smem)), qn(0), ltmask(lanemask_lt()),
+        slot(kEmitNoSlot), used(kEmitChunk), next_l0(fetch_slot(args.cursor)), has_next(true) {
+    if (threadIdx.x == 0) cs->emit = args;  // ordered before its first use by the barriers of the tile set-up
+  }
+  __device__ __forceinline__ void tile_begin(uint32_t, const Rec<T>*, bool) {}
+  // destination of this warp's next 32 rows (nullptr: beyond the capacity)
+  __device__ __forceinline__ uint2* claim32() {
+    if (used == kEmitChunk) {  // warp-uniform
+      slot = __shfl_sync(0xffffffffu, next_l0, 0);
+      used = 0;
+      next_l0 = fetch_slot(cs->emit.cursor);
+    }
+    uint2* base = slot < out_chunks ? out + (size_t)slot * kEmitChunk : emit_spill_rows(cs, slot);
+    uint2* dst = base ? base + used : nullptr;
+    used += 32;
+    return dst;
   }
   __device__ __forceinline__ void drain_exact_rows() {
     while (qn >= 32) {
       __syncwarp();
       qn -= 32;
-      put(true, q[qn + lane_id()]);
+      const uint2 row = q[qn + lane_id()];
+      uint2* dst = claim32();
+      if (dst) dst[lane_id()] = row;
       __syncwarp();
     }
   }
@@ -457,22 +504,147 @@ struct EmitConsumer {
     }
     drain_exact_rows();
   }
-  // pair_pf_kernels.cuh: one exactly decided pair per lane; its rows are nearly full (only pairs inside
-  // the f32 guard band can fail), so they go straight to the tile's output range
-  __device__ __forceinline__ void hit(bool h, T, uint32_t li, uint32_t lj) { put(h, make_uint2(li, lj)); }
+  // pair_pf_kernels.cuh: one exactly decided pair per lane
+  __device__ __forceinline__ void hit(bool h, T, uint32_t li, uint32_t lj) {
+    const unsigned b = __ballot_sync(0xffffffffu, h);
+    if (h) q[qn + __popc(b & ltmask)] = make_uint2(li, lj);
+    qn += __popc(b);
+    drain_exact_rows();
+  }
   __device__ __forceinline__ void add(uint32_t) {}
   __device__ __forceinline__ void chunk_end() {}
   template <int CMP>
   __device__ __forceinline__ void tile_end(uint32_t) {
-    __syncwarp();
-    if (qn > 0) {
-      put(lane_id() < qn, q[lane_id() < qn ? lane_id() : 0]);
-      qn = 0;
-    }
     __syncthreads();
   }
-  __device__ __forceinline__ void finish() {}
+  // the < 32 rows the warp is left with go behind its last store; what stays unused of its slots is recorded
+  __device__ __noinline__ void finish() {
+    const EmitOut& a = cs->emit;
+    auto note_partial = [&](uint32_t sl, uint32_t rows) {
+      const uint32_t i = atomicAdd(a.npartial, 1u);
+      if (i < a.partial_cap) a.partial[i] = make_uint2(sl, rows);
+    };
+    __syncwarp();
+    uint32_t nx = __shfl_sync(0xffffffffu, next_l0, 0);
+    if (qn > 0 && used == kEmitChunk) {
+      slot = nx;
+      used = 0;
+      has_next = false;
+    }
+    if (qn > 0) {
+      uint2* base = a.rows(slot);
+      if (base && lane_id() < qn) base[used + lane_id()] = q[lane_id()];
+      used += qn;
+    }
+    if (lane_id() == 0) {
+      if (slot != kEmitNoSlot && used < kEmitChunk) note_partial(slot, used);
+      if (has_next) note_partial(nx, 0u);
+    }
+  }
 };
+
+// what emit_fix_plan_kernel decides
+struct EmitFix {
+  unsigned long long total;   // rows of the list
+  uint32_t full;              // F: slots [0, F) are full after the moves, the partial rows follow at F * kEmitChunk
+  uint32_t moves;             // full slots behind F that move into partial slots in front of it
+  uint32_t npartial;
+  uint32_t ok;                // 0: longer than the capacity (nothing is moved) or internal table overflow (2)
+  unsigned long long tail_rows;  // rows of all partial slots
+};
+
+// One block.  partial[] = (slot, used) in arbitrary order; writes the packed offset of every partial slot
+// (poff[i], rows), the (source, destination) slot of every move, and the verdict.
+__global__ void __launch_bounds__(1024) emit_fix_plan_kernel(EmitOut o, unsigned long long cap_rows, uint32_t* __restrict__ poff,
+                                                             uint2* __restrict__ moves, EmitFix* __restrict__ fix) {
+  extern __shared__ unsigned char s_tailflag[];  // [partial_cap]: 1 = the slot F + t is a partial one
+  __shared__ uint32_t s_scan[32];
+  __shared__ uint32_t s_carry, s_nsrc, s_ndst;
+  const uint32_t noted = *o.npartial;
+  const uint32_t P = min(noted, o.partial_cap);
+  const unsigned long long R = *o.cursor;
+  const unsigned long long F = R - P;
+  if (threadIdx.x == 0) { s_carry = 0; s_nsrc = 0; s_ndst = 0; }
+  for (uint32_t t = threadIdx.x; t < P; t += blockDim.x) s_tailflag[t] = 0;
+  __syncthreads();
+  // packed offsets: exclusive scan of `used` in list order
+  for (uint32_t base = 0; base < P; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < P ? o.partial[i].y : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((int)lane_id() >= d) incl += up;
+    }
+    if (lane_id() == 31) s_scan[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = s_scan[threadIdx.x], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, wi, d);
+        if ((int)threadIdx.x >= d) wi += up;
+      }
+      s_scan[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    if (i < P) {
+      poff[i] = carry + s_scan[threadIdx.x >> 5] + incl - v;
+      const uint32_t slot = o.partial[i].x;
+      if (slot >= F) s_tailflag[slot - F] = 1;                       // slot < R = F + P
+      else moves[atomicAdd(&s_ndst, 1u)].y = slot;                   // a hole in front of F
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_scan[threadIdx.x >> 5] + incl;
+    __syncthreads();
+  }
+  // the full slots behind F fill the holes in front of it (as many of the one as of the other)
+  for (uint32_t t = threadIdx.x; t < P; t += blockDim.x)
+    if (!s_tailflag[t]) moves[atomicAdd(&s_nsrc, 1u)].x = (uint32_t)(F + t);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long total = F * kEmitChunk + s_carry;
+    fix->total = total;
+    fix->full = (uint32_t)F;
+    fix->moves = s_nsrc;
+    fix->npartial = P;
+    fix->tail_rows = s_carry;
+    uint32_t ok = 1;
+    if (total > cap_rows || R > (unsigned long long)o.out_chunks + o.spill_chunks) ok = 0;
+    if (noted > o.partial_cap || s_nsrc != s_ndst) ok = 2;
+    fix->ok = ok;
+  }
+}
+
+// rows of every partial slot -> tmp (packed)
+__global__ void __launch_bounds__(256) emit_fix_save_kernel(EmitOut o, const uint32_t* __restrict__ poff, const EmitFix* __restrict__ fix,
+                                                            uint2* __restrict__ tmp) {
+  if (fix->ok != 1) return;
+  for (uint32_t i = blockIdx.x; i < fix->npartial; i += gridDim.x) {
+    const uint2 pu = o.partial[i];
+    const uint2* src = o.rows(pu.x);
+    for (uint32_t k = threadIdx.x; k < pu.y; k += blockDim.x) tmp[poff[i] + k] = src[k];
+  }
+}
+// full slots from behind the end of the list -> the partial slots in front of it
+__global__ void __launch_bounds__(256) emit_fix_move_kernel(EmitOut o, const uint2* __restrict__ moves, const EmitFix* __restrict__ fix) {
+  if (fix->ok != 1) return;
+  for (uint32_t m = blockIdx.x; m < fix->moves; m += gridDim.x) {
+    const uint2* src = o.rows(moves[m].x);
+    uint2* dst = o.rows(moves[m].y);
+    for (uint32_t k = threadIdx.x; k < kEmitChunk; k += blockDim.x) dst[k] = src[k];
+  }
+}
+// tmp -> behind the last full slot
+__global__ void __launch_bounds__(256) emit_fix_pack_kernel(EmitOut o, const uint2* __restrict__ tmp, const EmitFix* __restrict__ fix) {
+  if (fix->ok != 1) return;
+  uint2* dst = o.out + (size_t)fix->full * kEmitChunk;
+  for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < fix->tail_rows;
+       k += (unsigned long long)gridDim.x * blockDim.x)
+    dst[k] = tmp[k];
+}
 
 // -- Lennard-Jones energy ----------------------------------------------------------------------
 // Hits are ~20 % of the tests, so evaluating lj() under the hit predicate would run the

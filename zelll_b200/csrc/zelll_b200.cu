@@ -45,6 +45,7 @@ struct DevBuf {
 
 constexpr uint32_t kMaxBboxBlocks = 148 * 4;
 constexpr uint32_t kMaxPairCtasPerSm = 8;
+constexpr uint32_t kMaxEmitCtasPerSm = 4;  // pair-list passes: bounds the partly filled output slots (emit_impl)
 constexpr uint64_t kMaxDenseCells = (1ull << 31) - 16;  // uint32 cell ids, table of 4 B entries
 
 // small device scratch block, zeroed at creation; re-armed by the kernels / rebuild
@@ -64,6 +65,7 @@ struct Misc {
   uint32_t slab_flag;      // bit0 = a particle outside the slab, bit1 = halo overflow, bit2 = box changed (speculative step)
   uint32_t halo_n;         // slab-local step: halo rows received (counted on the device)
   unsigned halo_ticket;    // p2p_halo_push_kernel: blocks finished (self re-arming)
+  EmitFix emit_fix;        // host copy only: verdict of the last pair-list pass
 };
 
 }  // namespace
@@ -127,6 +129,7 @@ struct zb_grid {
   DevBuf partials;  // bbox partials
   DevBuf keys_old, keys_new;
   DevBuf tile_counts, tile_offsets, block_energy, block_totals;
+  DevBuf emit_ctl, emit_tab, emit_spill, emit_tmp;  // zb_grid_pairs (emit_impl)
   DevBuf out_stage; // staging for host-destination outputs
   // sparse grids (sparse_kernels.cuh): compact sorted cells instead of the dense table
   bool sparse = false;
@@ -214,12 +217,11 @@ struct zb_grid {
   cudaEvent_t bbox_event = nullptr;  // fires when the bounding box has reached the host
   bool built_once = false;           // the table / scan state hold a previous build (sizes in ncells)
   uint32_t precleared = 0;           // cells whose table entries (+ scan state, counters) were cleared speculatively
-  // zb_grid_pairs: per-tile counts of the last sizing pass (still in tile_counts)
-  bool emit_cache_valid = false;
-  uint64_t emit_cache_build = 0, emit_cache_total = 0;
-  int emit_cache_cmp = 0;
-  double emit_cache_fc = 0.0;
-  PairPlan emit_cache_plan{};
+  // zb_grid_pairs: the length a sizing call found (same build, same filter: still exact)
+  bool pairs_sized = false;
+  uint64_t pairs_sized_build = 0, pairs_sized_total = 0;
+  int pairs_sized_cmp = 0;
+  double pairs_sized_fc = 0.0;
 
   // optional per-stage device timing (zb_grid_profile): cudaEvent pairs around the hot launches
   uint32_t profile = 0;  // bit s: record stage s
@@ -664,7 +666,6 @@ int rebuild_impl(zb_grid* g, const void* xyz_any, uint64_t n, const uint32_t* la
   }
   g->built = false;
   g->build_id++;
-  g->emit_cache_valid = false;
   g->precleared = 0;
   if (g->info_pending) {  // the previous build's counters are about to be overwritten
     ZB_CUDA(cudaEventSynchronize(g->info_event));
@@ -950,8 +951,6 @@ int sparse_tile_list(zb_grid* g, const PairPlan& pl, PairParams<T>& p) {
     g->tile_list_build = g->build_id;
     g->tile_list_cells = pl.tile_cells;
     g->tile_list_rows = pl.row_tiles;
-    // the list is filled in atomic arrival order: per-work-item counts of an earlier list are void
-    g->emit_cache_valid = false;
   }
   p.tile_list = buf + 1;
   p.tile_list_n = buf;
@@ -989,7 +988,7 @@ int launch_pairs(zb_grid* g, int cmp, PairPlan& pl, const PairParams<T>& p_in, t
     if (occ == 0) {
       ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPairThreads, smem));
-      occ = std::max(1, std::min(occ, (int)kMaxPairCtasPerSm));
+      occ = std::max(1, std::min(occ, (int)(Consumer::kStage == 5 ? kMaxEmitCtasPerSm : kMaxPairCtasPerSm)));
       g->occ_cache.push_back({key, smem, occ});
     }
     const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(pl.ntiles, (uint32_t)g->sm_count * (uint32_t)occ));
@@ -1080,20 +1079,16 @@ int finalize(zb_grid* g, bool with_energy, uint32_t nblocks) {
 }
 
 template <class T>
-int pair_count_impl(zb_grid* g, int cmp, double fc, bool per_tile, PairPlan* plan_out) {
-  // the sizing pass of zb_grid_pairs (per_tile) must tile exactly like the emit pass that follows it
-  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, CountConsumer<T>::kPfWarpSmemBytes, cmp, fc, per_tile ? 4u : 1u);
+int pair_count_impl(zb_grid* g, int cmp, double fc) {
+  PairPlan pl = plan_pairs<T>(g, CountConsumer<T>::kWarpSmemBytes, CountConsumer<T>::kPfWarpSmemBytes, cmp, fc, 1u);
   ZB_TRY(reserve(g, g->block_totals, (size_t)pl.blocks * 8));
-  if (per_tile) ZB_TRY(reserve(g, g->tile_counts, ((size_t)pl.ntiles + 1) * 8));
   typename CountConsumer<T>::Args a;
-  a.tile_counts = per_tile ? static_cast<unsigned long long*>(g->tile_counts.p) : nullptr;
+  a.tile_counts = nullptr;
   a.block_totals = static_cast<unsigned long long*>(g->block_totals.p);
-  if (per_tile) ZB_CUDA(cudaMemsetAsync(g->tile_counts.p, 0, ((size_t)pl.ntiles + 1) * 8, g->stream));
   // every launched block writes its slot of block_totals (finish()): clear only when nothing runs
   if (pl.ntiles) ZB_TRY((launch_pairs<T, CountConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), a)));
   else ZB_CUDA(cudaMemsetAsync(g->block_totals.p, 0, (size_t)pl.blocks * 8, g->stream));
   ZB_TRY(finalize(g, false, pl.blocks));
-  if (plan_out) *plan_out = pl;
   return ZB_OK;
 }
 
@@ -1116,24 +1111,47 @@ int lj_impl(zb_grid* g, int cmp, double fc, uint32_t* blocks_out = nullptr) {
   return ZB_OK;
 }
 
+// One pass over the pairs into `out_dev` (room for cap_rows rows); the list's length arrives in h_fix.
+// See EmitConsumer (pair_kernels.cuh) for the slot scheme and the emit_fix_* kernels that close its holes.
 template <class T>
-int emit_impl(zb_grid* g, int cmp, double fc, const PairPlan& pl, uint2* out_dev) {
-  // per-tile arrays are indexed by work item: all tiles, or (sparse boxes) the listed ones
-  const bool sparse = g->tile_list_build == g->build_id && g->tile_list_cells == pl.tile_cells &&
-                      g->tile_list_rows == pl.row_tiles && g->tile_list.p &&
-                      !(pl.ntiles < 4096 || g->n * 8 > (uint64_t)g->ncells);
-  tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), pl.ntiles,
-                                                 sparse ? static_cast<const uint32_t*>(g->tile_list.p) : nullptr,
-                                                 static_cast<unsigned long long*>(g->tile_offsets.p));
-  g->launches++;
-  typename EmitConsumer<T>::Args a;
-  a.tile_offsets = static_cast<const unsigned long long*>(g->tile_offsets.p);
-  a.out = out_dev;
-  PairPlan pe = pl;
-  pe.smem = pl.prefilter ? pf_smem_bytes(EmitConsumer<T>::kPfWarpSmemBytes)
-                         : pl.smem - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
-  pe.smem_exact = pl.smem_exact - kPairWarps * CountConsumer<T>::kWarpSmemBytes + kPairWarps * EmitConsumer<T>::kWarpSmemBytes;
-  if (pl.ntiles) ZB_TRY((launch_pairs<T, EmitConsumer<T>>(g, cmp, pe, pair_params<T>(g, pl, fc), a)));
+int emit_impl(zb_grid* g, int cmp, double fc, uint2* out_dev, uint64_t cap_rows, EmitFix* h_fix) {
+  PairPlan pl = plan_pairs<T>(g, EmitConsumer<T>::kWarpSmemBytes, EmitConsumer<T>::kPfWarpSmemBytes, cmp, fc, 4u);
+  // every warp of every launch leaves at most two partly filled slots (EmitConsumer::finish); launch_pairs runs
+  // at most two launches of at most kMaxEmitCtasPerSm CTAs per SM
+  const uint32_t pcap = 2u * kPairWarps * 2u * (uint32_t)g->sm_count * kMaxEmitCtasPerSm;
+  // control block: cursor (8), npartial (4, padded to 8), EmitFix; tables: partial[pcap], moves[pcap], poff[pcap]
+  ZB_TRY(reserve(g, g->emit_ctl, 16 + sizeof(EmitFix)));
+  ZB_TRY(reserve(g, g->emit_tab, (size_t)pcap * (8 + 8 + 4)));
+  ZB_TRY(reserve(g, g->emit_spill, (size_t)pcap * kEmitChunk * 8));
+  ZB_TRY(reserve(g, g->emit_tmp, (size_t)pcap * kEmitChunk * 8));
+  unsigned char* ctl = static_cast<unsigned char*>(g->emit_ctl.p);
+  unsigned char* tab = static_cast<unsigned char*>(g->emit_tab.p);
+  ZB_CUDA(cudaMemsetAsync(ctl, 0, 16, g->stream));
+  EmitOut o;
+  o.out = out_dev;
+  o.spill = static_cast<uint2*>(g->emit_spill.p);
+  o.out_chunks = (uint32_t)std::min<uint64_t>(cap_rows / kEmitChunk, 0x7fffffffull);
+  o.spill_chunks = pcap;
+  o.cursor = reinterpret_cast<unsigned long long*>(ctl);
+  o.npartial = reinterpret_cast<uint32_t*>(ctl + 8);
+  o.partial = reinterpret_cast<uint2*>(tab);
+  o.partial_cap = pcap;
+  uint2* moves = reinterpret_cast<uint2*>(tab + (size_t)pcap * 8);
+  uint32_t* poff = reinterpret_cast<uint32_t*>(tab + (size_t)pcap * 16);
+  EmitFix* fix = reinterpret_cast<EmitFix*>(ctl + 16);
+  if (pl.ntiles) ZB_TRY((launch_pairs<T, EmitConsumer<T>>(g, cmp, pl, pair_params<T>(g, pl, fc), o)));
+  {
+    StageSpan span(g, EmitConsumer<T>::kStage);
+    emit_fix_plan_kernel<<<1, 1024, (size_t)pcap, g->stream>>>(o, cap_rows, poff, moves, fix);
+    emit_fix_save_kernel<<<g->sm_count * 2, 256, 0, g->stream>>>(o, poff, fix, static_cast<uint2*>(g->emit_tmp.p));
+    emit_fix_move_kernel<<<g->sm_count * 2, 256, 0, g->stream>>>(o, moves, fix);
+    emit_fix_pack_kernel<<<g->sm_count * 2, 256, 0, g->stream>>>(o, static_cast<const uint2*>(g->emit_tmp.p), fix);
+  }
+  g->launches += 4;
+  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(cudaMemcpyAsync(&g->h_misc->emit_fix, fix, sizeof(EmitFix), cudaMemcpyDeviceToHost, g->stream));
+  ZB_CUDA(cudaStreamSynchronize(g->stream));
+  *h_fix = g->h_misc->emit_fix;
   return ZB_OK;
 }
 
@@ -1235,7 +1253,7 @@ void zb_grid_destroy(zb_grid* g) {
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   DevBuf* bufs[] = {&g->in,        &g->labels_in,   &g->table,        &g->sorted,       &g->scan_state,
-                    &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets,
+                    &g->partials,  &g->keys_old,    &g->keys_new,     &g->tile_counts,  &g->tile_offsets, &g->emit_ctl, &g->emit_tab, &g->emit_spill, &g->emit_tmp,
                     &g->block_energy, &g->block_totals, &g->out_stage, &g->tile_list, &g->pf_list, &g->skeys[0], &g->skeys[1], &g->sidx[0], &g->sidx[1], &g->shist, &g->sflags,
                     &g->ukeys, &g->ubegin, &g->halo_send, &g->halo_recv, &g->halo_labels,
                     &g->red};
@@ -1644,8 +1662,8 @@ int zb_grid_pair_count(zb_grid* g, int cmp, double filter_cutoff, uint64_t* out)
   ZB_TRY(check_built(g));
   if (!out) return fail(g, ZB_ERR_BAD_ARG, "out is NULL");
   if (cmp < 0 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
-  if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff, false, nullptr));
-  else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff, false, nullptr));
+  if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff));
+  else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff));
   return deliver(g, out, &g->misc->pair_total, 8);
 }
 
@@ -1654,43 +1672,52 @@ int zb_grid_pairs(zb_grid* g, int cmp, double filter_cutoff, uint32_t* ij, uint6
   ZB_TRY(check_built(g));
   if (!n_out) return fail(g, ZB_ERR_BAD_ARG, "n_out is NULL");
   if (cmp < 0 || cmp > 2) return fail(g, ZB_ERR_BAD_ARG, "bad cmp %d", cmp);
-  // pass 1 (per-tile counts) is reused when the caller sizes first and then fetches: same grid
-  // build, same filter -> the cached tile counts are still exact
-  PairPlan pl;
-  uint64_t total;
-  if (g->emit_cache_valid && g->emit_cache_build == g->build_id && g->emit_cache_cmp == cmp &&
-      g->emit_cache_fc == filter_cutoff) {
-    pl = g->emit_cache_plan;
-    total = g->emit_cache_total;
-  } else {
-    g->emit_cache_valid = false;
-    if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff, true, &pl));
-    else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff, true, &pl));
+  // the length of the list, if an earlier call on the same build and filter already counted it
+  bool known = g->pairs_sized && g->pairs_sized_build == g->build_id && g->pairs_sized_cmp == cmp &&
+               g->pairs_sized_fc == filter_cutoff;
+  uint64_t total = known ? g->pairs_sized_total : 0;
+  auto size_it = [&]() -> int {
+    if (g->dtype == ZB_F32) ZB_TRY(pair_count_impl<float>(g, cmp, filter_cutoff));
+    else ZB_TRY(pair_count_impl<double>(g, cmp, filter_cutoff));
     ZB_CUDA(cudaMemcpyAsync(&g->h_misc->pair_total, &g->misc->pair_total, 8, cudaMemcpyDeviceToHost, g->stream));
     ZB_CUDA(cudaStreamSynchronize(g->stream));
     total = g->h_misc->pair_total;
-    g->emit_cache_plan = pl;
-    g->emit_cache_total = total;
-    g->emit_cache_build = g->build_id;
-    g->emit_cache_cmp = cmp;
-    g->emit_cache_fc = filter_cutoff;
-    g->emit_cache_valid = true;
+    g->pairs_sized = known = true;
+    g->pairs_sized_build = g->build_id;
+    g->pairs_sized_cmp = cmp;
+    g->pairs_sized_fc = filter_cutoff;
+    g->pairs_sized_total = total;
+    return ZB_OK;
+  };
+  const bool dev_out = ij && is_device_ptr(ij);
+  // a sizing call (no buffer), or a host destination: count first (the staging buffer gets the exact size, and
+  // the count pass is small change beside the copy to the host).  A device destination with room is written in
+  // ONE pass, no count in front of it.
+  if (!known && (!ij || cap == 0 || !dev_out)) ZB_TRY(size_it());
+  if (known) {
+    *n_out = total;
+    if (total > cap || (total && !ij))
+      return fail(g, ZB_ERR_CAPACITY, "pair list needs %llu rows, capacity is %llu", (unsigned long long)total,
+                  (unsigned long long)cap);
+    if (total == 0) return ZB_OK;
   }
-  *n_out = total;
-  if (total > cap || (total && !ij))
-    return fail(g, ZB_ERR_CAPACITY, "pair list needs %llu rows, capacity is %llu", (unsigned long long)total,
-                (unsigned long long)cap);
-  if (total == 0) return ZB_OK;
-  const bool dev_out = is_device_ptr(ij);
+  const uint64_t room = known ? total : cap;
   uint2* dst = reinterpret_cast<uint2*>(ij);
   if (!dev_out) {
-    ZB_TRY(reserve(g, g->out_stage, total * 8));
+    ZB_TRY(reserve(g, g->out_stage, room * 8));
     dst = static_cast<uint2*>(g->out_stage.p);
   }
-  ZB_TRY(reserve(g, g->tile_offsets, ((size_t)pl.ntiles + 1) * 8));
-  if (g->dtype == ZB_F32) ZB_TRY(emit_impl<float>(g, cmp, filter_cutoff, pl, dst));
-  else ZB_TRY(emit_impl<double>(g, cmp, filter_cutoff, pl, dst));
-  if (!dev_out) ZB_TRY(deliver(g, ij, dst, total * 8));
+  EmitFix fix;
+  if (g->dtype == ZB_F32) ZB_TRY(emit_impl<float>(g, cmp, filter_cutoff, dst, room, &fix));
+  else ZB_TRY(emit_impl<double>(g, cmp, filter_cutoff, dst, room, &fix));
+  *n_out = fix.total;
+  if (fix.ok == 2 || (known && fix.total != total))
+    return fail(g, ZB_ERR_CUDA, "pair list: slot bookkeeping failed (%llu rows, %llu expected, %u partial slots)",
+                (unsigned long long)fix.total, (unsigned long long)total, fix.npartial);
+  if (fix.ok != 1)
+    return fail(g, ZB_ERR_CAPACITY, "pair list needs %llu rows, capacity is %llu", (unsigned long long)fix.total,
+                (unsigned long long)cap);
+  if (!dev_out && fix.total) ZB_TRY(deliver(g, ij, dst, fix.total * 8));
   return ZB_OK;
 }
 
@@ -1769,7 +1796,6 @@ int zb_grid_query_neighbors(zb_grid* g, const void* queries, uint64_t nq, int cm
   // pass 1: counts -> exclusive scan -> offsets
   if (g->dtype == ZB_F32) ZB_TRY(run(float(), false, nullptr));
   else ZB_TRY(run(double(), false, nullptr));
-  g->emit_cache_valid = false;  // tile_counts is reused below
   ZB_TRY(reserve(g, g->tile_counts, (nq + 1) * 8));
   ZB_CUDA(cudaMemcpyAsync(g->tile_counts.p, doff, nq * 8, cudaMemcpyDeviceToDevice, g->stream));
   tile_offsets_kernel<<<1, 1024, 0, g->stream>>>(static_cast<const unsigned long long*>(g->tile_counts.p), (uint32_t)nq,
