@@ -496,6 +496,32 @@ def run_ours(args):
                    "algorithmic_bytes_per_particle": {"rebuild": 40.8, "lj": 12.8}}
         del g32, p32, q32
 
+    # ---- the materialised neighbour list (zb_grid_pairs; python/src/lib.rs:283-315 collects the same list on the
+    # host): rebuild + ONE pass over the pairs into a device buffer with head-room, outside the headline.  Rows
+    # = the pairs the LJ step keeps, so the same pairs/s metric applies (8 B written per pair).
+    list_leg = None
+    if not distributed and not args.no_pair_list and n_per * 17 * 8 < 40e9:
+        cap_rows = int(pairs * 1.05) + 4096
+        def list_step():
+            with torch.cuda.stream(stream):  # particle_pairs_device runs on torch's current stream
+                grid.rebuild_mut(dev_pts, None)
+                return grid.particle_pairs_device(CUTOFF, "lt", capacity=cap_rows)
+        for _ in range(3):
+            rows = list_step()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(steps, 10))
+        e0.record(stream)
+        for _ in range(reps):
+            rows = list_step()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        ms_list = e0.elapsed_time(e1) / reps
+        list_leg = {"rebuild_plus_pair_list_ms": ms_list, "rows": int(rows.shape[0]), "rows_match_lj_pairs": bool(rows.shape[0] == pairs),
+                    "pairs_per_s": rows.shape[0] / (ms_list * 1e-3), "bytes_written": int(rows.shape[0]) * 8,
+                    "passes_over_the_pairs": 1}
+        del rows
+
     ms_step = ms_total / steps
     ms_step_e2e = ms_e2e / steps
     if rank != 0:
@@ -579,6 +605,8 @@ def run_ours(args):
         line["sustained"] = sustained
     if f32_leg is not None:
         line["f32"] = f32_leg
+    if list_leg is not None:
+        line["pair_list"] = list_leg
     if parity is not None:
         line["parity_check"] = parity
     print(json.dumps(line))
@@ -602,6 +630,7 @@ def main():
     ap.add_argument("--sustained-s", type=float, default=2.0,
                     help="seconds of back-to-back steps timed after the K-step region (reported as `sustained`; 0 = skip)")
     ap.add_argument("--no-f32", action="store_true", help="skip the f32 leg")
+    ap.add_argument("--no-pair-list", action="store_true", help="skip the materialised pair-list leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (very large --n-per-gpu runs)")
     args = ap.parse_args()
