@@ -224,7 +224,8 @@ int zb_grid_pair_count(zb_grid* g, int cmp, double filter_cutoff, uint64_t* out)
  * ij == NULL or cap == 0 is a sizing call: *n_out = rows needed (ZB_ERR_CAPACITY unless that is 0).
  * A DEVICE buffer is filled in one pass over the pairs, without a counting pass in front of it; if it turns
  * out too small: ZB_ERR_CAPACITY, *n_out = needed, and the buffer's contents are unspecified.  A host buffer
- * that is too small is left untouched. */
+ * that is too small is left untouched.  Rows [*n_out, cap) of a device buffer are scratch in either case;
+ * nothing is written at or beyond row cap. */
 int zb_grid_pairs(zb_grid* g, int cmp, double filter_cutoff, uint32_t* ij, uint64_t cap,
                   uint64_t* n_out);
 

@@ -845,6 +845,34 @@ def test_pair_list_single_pass_into_device_buffer(zb, dtype):
     torch.cuda.synchronize()
 
 
+def test_pair_list_never_writes_beyond_capacity(zb):
+    """Own bounds check of the one-pass list (compute-sanitizer is not available on the GPU pool): a guard region
+    behind the capacity keeps its canary for capacities that are exact, off the 512-row slot size, and too small."""
+    import ctypes as C
+    import torch
+    from zelll_b200 import _ffi
+
+    pts, cutoff = _cloud("lj", 30000, np.float64)
+    cg = zb.CellGrid(pts, cutoff)
+    m = cg.pair_count(cutoff, "lt")
+    want = canonical_pairs(cg.particle_pairs(cutoff, "lt"))
+    guard = 8192
+    for cap in (m, m + 1, m + 511, m + 513, 2 * m + 77, m - 1, m // 3, 511, 1):
+        cg.rebuild(pts, cutoff)
+        buf = torch.full((cap + guard, 2), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        cg.use_stream(torch.cuda.current_stream().cuda_stream)
+        n_out = C.c_uint64(0)
+        rc = cg._lib.zb_grid_pairs(cg._h, _ffi.CMP_LT, float(cutoff), buf.data_ptr(), cap, C.byref(n_out))
+        torch.cuda.synchronize()
+        assert int(n_out.value) == m
+        assert bool((buf[cap:] == 0x5A5A5A5A).all()), cap
+        if cap >= m:
+            assert rc == _ffi.OK
+            assert np.array_equal(canonical_pairs(buf[:m].cpu().numpy().view(np.uint32)), want)
+        else:
+            assert rc == _ffi.ERR_CAPACITY
+
+
 def test_pair_list_full_size_single_pass(zb):
     """n = 10^7: 1.6e8 rows written in one pass into a buffer with head-room.  Size-independent properties that
     pin the set: as many rows as the exact count, all rows distinct, every row a pair inside the cutoff."""
